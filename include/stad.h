@@ -1,0 +1,171 @@
+/* libstad.so — C ABI of the B200-native (sm_100a) Video-ViT encoder forward used by simple-tad.
+ *
+ * The reference (tue-mps/simple-tad) has no FFI: the boundary this path sits behind is the Python nn.Module API of
+ * modeling_finetune.py / modeling_pretrain.py / flash_attention_class.py.  Each entry point below replaces the
+ * library kernels one reference call site reaches (cuDNN / cuBLAS / ATen / flash-attn 2); the call site is cited as
+ * file:line relative to the reference root (mf = modeling_finetune.py, mp = modeling_pretrain.py,
+ * fac = flash_attention_class.py, ri = run_inference.py, ris = run_inference_simple.py).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; the caller (PyTorch) owns all memory, the library
+ *     never allocates or frees user-visible memory and never synchronises the device;
+ *   - "bf16" buffers are row-major __nv_bfloat16; float buffers are fp32;
+ *   - every call launches asynchronously on `stream` (a cudaStream_t passed as void*), is CUDA-graph capturable,
+ *     and returns 0 or a negative STAD_E_* code; stad_last_error() returns the thread-local message;
+ *   - there is no CPU path and no non-sm_100 path: stad_init() refuses other architectures.
+ */
+#ifndef STAD_H_
+#define STAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STAD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define STAD_API __attribute__((visibility("default")))
+#else
+#define STAD_API
+#endif
+
+typedef void* stad_stream_t; /* cudaStream_t */
+
+enum {
+  STAD_OK = 0,
+  STAD_E_SHAPE = -1, /* unsupported / inconsistent sizes            (reference: Python assert, mf:188)   */
+  STAD_E_ALIGN = -2, /* pointer or leading dimension not 16-byte aligned                                 */
+  STAD_E_ARCH = -3,  /* device is not compute capability 10.x                                            */
+  STAD_E_CUDA = -4   /* a CUDA runtime / driver call failed                                              */
+};
+
+/* Epilogues of stad_ln_gemm. */
+enum {
+  STAD_EPI_BIAS = 0,     /* y = LN(x) W^T + b                     -> QKV projection, mf:92 / mf:119            */
+  STAD_EPI_BIAS_GELU = 1 /* y = GELU_erf(LN(x) W^T + b)           -> Mlp.fc1 + nn.GELU, mf:48-49               */
+};
+
+/* Where the clips of a batch live. */
+enum {
+  STAD_IN_CLIPS = 0, /* x[B, C, T, H, W] bf16 — the tensor VisionTransformer.forward receives (mf:332)          */
+  STAD_IN_FRAMES = 1 /* frames[F, C, H, W] bf16 of ONE video; clip b = frames[start + b*stride, +T) — the
+                        sliding window of ri:69-109 / ris:428-465 / dota.py:204-223 without materialising it */
+};
+
+typedef struct stad_input {
+  const void* data; /* bf16 */
+  int32_t mode;     /* STAD_IN_CLIPS | STAD_IN_FRAMES */
+  int32_t n_frames; /* FRAMES: F (number of frames resident); CLIPS: ignored */
+  int32_t start;    /* FRAMES: first frame of clip 0 */
+  int32_t stride;   /* FRAMES: frame step between consecutive clips (1 = every window, dota.py:209) */
+} stad_input;
+
+/* Geometry of one model (PatchEmbed mf:172-183, VisionTransformer mf:211-234). */
+typedef struct stad_dims {
+  int32_t img_h, img_w; /* 224 */
+  int32_t patch;        /* 16 */
+  int32_t tubelet;      /* 2 */
+  int32_t frames;       /* 16  (all_frames) */
+  int32_t in_chans;     /* 3 */
+  int32_t dim;          /* D: 384 / 768 / 1024 */
+  int32_t depth;        /* L */
+  int32_t heads;        /* H  (head dim is fixed at 64) */
+  int32_t hidden;       /* mlp hidden = 4 D */
+  int32_t num_classes;  /* 2 (0 = encoder only: return tokens after `norm`, mp:107) */
+} stad_dims;
+
+/* One transformer Block (mf:137-166) after weight preparation:
+ *   LayerNorm gamma is folded into the following weight, beta into its bias (W' = W diag(gamma), b' = b + W beta),
+ *   colsum[n] = sum_k bf16(W'[n,k]) — so  LN(x) W^T + b == rstd * (x W'^T - mean * colsum) + b'   (SURVEY §7 step 4). */
+typedef struct stad_block {
+  const void* w_qkv;   /* [3D, D] bf16, norm1-folded;  rows q|k|v (mf:69)                       */
+  const float* b_qkv;  /* [3D] = cat(q_bias, 0, v_bias) + W beta1   (mf:88-90)                  */
+  const float* cs_qkv; /* [3D] */
+  const void* w_proj;  /* [D, D] bf16 (mf:78)  */
+  const float* b_proj; /* [D] */
+  const void* w_fc1;   /* [4D, D] bf16, norm2-folded (mf:42) */
+  const float* b_fc1;  /* [4D] */
+  const float* cs_fc1; /* [4D] */
+  const void* w_fc2;   /* [D, 4D] bf16 (mf:44) */
+  const float* b_fc2;  /* [D] */
+} stad_block;
+
+typedef struct stad_model {
+  stad_dims dims;
+  const void* w_patch;      /* [D, C*tubelet*patch*patch] bf16 = Conv3d weight flattened (c,dt,dh,dw)  (mf:181-183) */
+  const float* pos_bias;    /* [N, D] fp32 = sinusoid table (mf:195-205) + conv bias                               */
+  const stad_block* blocks; /* HOST array of `depth` entries                                                       */
+  const float* norm_g;      /* final LayerNorm: fc_norm (mf:270, classifier) or norm (mp:59, encoder)              */
+  const float* norm_b;
+  const float* w_head; /* [num_classes, D] fp32 (mf:272) or NULL */
+  const float* b_head; /* [num_classes] */
+  float eps;           /* 1e-6 (mf:342) */
+  float attn_scale;    /* head_dim ** -0.5 (mf:67) */
+} stad_model;
+
+/* ---- library ------------------------------------------------------------------------------------------------- */
+STAD_API int stad_abi_version(void);
+/* Binds nothing, checks that `device` is sm_100 and raises the kernels' shared-memory limits. Idempotent. */
+STAD_API int stad_init(int device);
+STAD_API const char* stad_last_error(void);
+
+/* ---- element / row kernels (HBM-bound) ------------------------------------------------------------------------ */
+/* fp32 -> bf16 cast of a clip batch; stands in for torch.cuda.amp.autocast's input cast (eff:428, te:177). */
+STAD_API int stad_cast_f32_bf16(const float* x, void* y, size_t n, stad_stream_t stream);
+
+/* Per-row LayerNorm statistics (mean, rstd) of x[M, D] bf16 -> stats[M] float2.   nn.LayerNorm stats, mf:143/149. */
+STAD_API int stad_row_stats(const void* x, float* stats, int M, int D, float eps, stad_stream_t stream);
+
+/* Full LayerNorm y = (x - mean) * rstd * g + b of x[M, D] bf16 -> y[M, D] fp32.   encoder `norm`, mp:107. */
+STAD_API int stad_layernorm(const void* x, const float* g, const float* b, float* y, int M, int D, float eps,
+                   stad_stream_t stream);
+
+/* mean over tokens -> fc_norm -> head (-> softmax).   mf:325-326, mf:334, ris:381.
+ * x[B, N, D] bf16; logits[B, C] fp32; probs[B, C] fp32 or NULL; scratch: >= B * 16 * D floats. */
+STAD_API int stad_pool_norm_head(const void* x, const float* g, const float* b, const float* w_head, const float* b_head,
+                        float* logits, float* probs, float* scratch, int B, int N, int D, int C, float eps,
+                        stad_stream_t stream);
+
+/* ---- tensor-core kernels (tcgen05 / TMEM / TMA) ---------------------------------------------------------------- */
+/* Tubelet patch embedding: Conv3d(k = s = (tubelet, patch, patch)) as an im2col-free GEMM + pos/bias table add.
+ *   PatchEmbed.forward mf:185-191 and the position add mf:312-313 (mp:93-95 for the encoder).
+ * tok_idx == NULL : all N tokens of every clip, out[B*N, D] bf16, token order (t', h', w').
+ * tok_idx != NULL : int32[B, n_tok] token ids (row-major order of surviving tokens, mp:98); only those tokens are
+ *                   embedded; `gather` must hold B*n_tok*K bf16 of scratch. */
+STAD_API int stad_patch_embed(const stad_input* in, const void* w, const float* pos_bias, const int32_t* tok_idx, void* out,
+                     void* gather, const stad_dims* dims, int B, int n_tok, stad_stream_t stream);
+
+/* y[M, N] = epilogue( rstd[m] * (x W'^T - mean[m] * colsum[n]) + bias[n] ), bf16 in / bf16 out, fp32 accumulate.
+ *   norm1 -> qkv (mf:92,119);  norm2 -> fc1 -> GELU (mf:48-49).   stats from stad_row_stats. */
+STAD_API int stad_ln_gemm(const void* x, const float* stats, const void* w, const float* bias, const float* colsum,
+                 int epilogue, void* out, int M, int N, int K, stad_stream_t stream);
+
+/* y[M, N] = a W^T + bias (+ residual), bf16 in / bf16 out.   attn.proj + residual (mf:104/128, mf:161);
+ *   fc2 + residual (mf:52, mf:162).  residual may be NULL (plain Linear) and may alias out. */
+STAD_API int stad_gemm_bias_residual(const void* a, const void* w, const float* bias, const void* residual, void* out, int M,
+                            int N, int K, stad_stream_t stream);
+
+/* Joint space-time softmax(q k^T * scale) v over packed qkv[B, S, 3, H, 64] bf16 -> out[B, S, H*64] bf16.
+ *   Same tensor contract as FlashAttention.forward (fac:26-51, qkv "(B, S, 3, H, D)") and the math of
+ *   Attention._naive_attn mf:93-103.  No N x N matrix is written to memory. */
+STAD_API int stad_attention(const void* qkv, void* out, int B, int H, int S, float scale, stad_stream_t stream);
+
+/* ---- whole forward ---------------------------------------------------------------------------------------------- */
+/* Bytes of scratch stad_vit_forward needs for a batch of B clips with n_tok tokens each. */
+STAD_API size_t stad_workspace_bytes(const stad_dims* dims, int B, int n_tok);
+
+/* VisionTransformer.forward (mf:308-335) / PretrainVisionTransformerEncoder.forward_features (mp:91-108).
+ *   tok_idx NULL  -> classifier path: logits[B, C] (+ probs[B, C] if non-NULL).
+ *   tok_idx given -> visible-token encoder path: tokens_out[B, n_tok, D] fp32 after `norm`; logits may be NULL.
+ * Returns the number of kernels launched (>= 0) or a negative error. */
+STAD_API int stad_vit_forward(const stad_model* model, const stad_input* in, const int32_t* tok_idx, int B, int n_tok,
+                     float* logits, float* probs, float* tokens_out, void* workspace, size_t workspace_bytes,
+                     stad_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAD_H_ */

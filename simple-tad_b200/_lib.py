@@ -1,0 +1,238 @@
+"""ctypes binding of libstad.so (include/stad.h).  PyTorch is plumbing here: it owns device memory and streams and
+hands raw pointers to the C ABI.  There is no fallback: if the library is missing or the device is not sm_100 every
+entry point raises."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstad.so")
+
+STAD_OK, STAD_E_SHAPE, STAD_E_ALIGN, STAD_E_ARCH, STAD_E_CUDA = 0, -1, -2, -3, -4
+STAD_EPI_BIAS, STAD_EPI_BIAS_GELU = 0, 1
+STAD_IN_CLIPS, STAD_IN_FRAMES = 0, 1
+
+EXPORTS = (
+    "stad_abi_version", "stad_init", "stad_last_error", "stad_cast_f32_bf16", "stad_row_stats", "stad_layernorm",
+    "stad_pool_norm_head", "stad_patch_embed", "stad_ln_gemm", "stad_gemm_bias_residual", "stad_attention",
+    "stad_workspace_bytes", "stad_vit_forward",
+)
+
+
+class StadInput(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("mode", C.c_int32), ("n_frames", C.c_int32), ("start", C.c_int32),
+                ("stride", C.c_int32)]
+
+
+class StadDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("img_h", "img_w", "patch", "tubelet", "frames", "in_chans", "dim", "depth",
+                                          "heads", "hidden", "num_classes")]
+
+
+class StadBlock(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w_qkv", "b_qkv", "cs_qkv", "w_proj", "b_proj", "w_fc1", "b_fc1", "cs_fc1",
+                                           "w_fc2", "b_fc2")]
+
+
+class StadModel(C.Structure):
+    _fields_ = [("dims", StadDims), ("w_patch", C.c_void_p), ("pos_bias", C.c_void_p), ("blocks", C.POINTER(StadBlock)),
+                ("norm_g", C.c_void_p), ("norm_b", C.c_void_p), ("w_head", C.c_void_p), ("b_head", C.c_void_p),
+                ("eps", C.c_float), ("attn_scale", C.c_float)]
+
+
+_lib = None
+_inited_devices = set()
+
+
+def load():
+    """dlopen libstad.so (no CUDA call is made here, so this also works on a CPU-only box)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(simple-tad_b200 has no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    protos = {
+        "stad_abi_version": (C.c_int, []),
+        "stad_init": (C.c_int, [i32]),
+        "stad_last_error": (C.c_char_p, []),
+        "stad_cast_f32_bf16": (C.c_int, [vp, vp, sz, vp]),
+        "stad_row_stats": (C.c_int, [vp, vp, i32, i32, f32, vp]),
+        "stad_layernorm": (C.c_int, [vp, vp, vp, vp, i32, i32, f32, vp]),
+        "stad_pool_norm_head": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]),
+        "stad_patch_embed": (C.c_int, [C.POINTER(StadInput), vp, vp, vp, vp, vp, C.POINTER(StadDims), i32, i32, vp]),
+        "stad_ln_gemm": (C.c_int, [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp]),
+        "stad_gemm_bias_residual": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+        "stad_attention": (C.c_int, [vp, vp, i32, i32, i32, f32, vp]),
+        "stad_workspace_bytes": (sz, [C.POINTER(StadDims), i32, i32]),
+        "stad_vit_forward": (C.c_int, [C.POINTER(StadModel), C.POINTER(StadInput), vp, i32, i32, vp, vp, vp, vp, sz,
+                                       vp]),
+    }
+    for name, (res, args) in protos.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().stad_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    """Map a negative STAD_E_* code to the reference's error convention (Python exceptions, mf:188)."""
+    if rc >= 0:
+        return rc
+    msg = f"{what}: {last_error()} (code {rc})"
+    if rc in (STAD_E_SHAPE, STAD_E_ALIGN):
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def init(device=None):
+    """stad_init on the tensor's / current device. Raises unless the device is an sm_100 GPU."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("simple-tad_b200 needs a CUDA device (sm_100a); there is no CPU path")
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _inited_devices:
+        with torch.cuda.device(idx):
+            check(load().stad_init(idx), "stad_init")
+        _inited_devices.add(idx)
+    return idx
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _req(t, dtype, name):
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError(f"{name}: expected a contiguous CUDA tensor of {dtype}, got {t.dtype} on {t.device} "
+                         f"contiguous={t.is_contiguous()}")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------- thin op wrappers
+def cast_f32_bf16(x):
+    init(x.device)
+    _req(x, torch.float32, "x")
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(load().stad_cast_f32_bf16(ptr(x), ptr(y), x.numel(), stream_ptr()), "stad_cast_f32_bf16")
+    return y
+
+
+def row_stats(x, eps):
+    init(x.device)
+    _req(x, torch.bfloat16, "x")
+    M, D = x.shape
+    stats = torch.empty(M, 2, dtype=torch.float32, device=x.device)
+    check(load().stad_row_stats(ptr(x), ptr(stats), M, D, eps, stream_ptr()), "stad_row_stats")
+    return stats
+
+
+def layernorm(x, g, b, eps):
+    init(x.device)
+    _req(x, torch.bfloat16, "x")
+    M, D = x.shape
+    y = torch.empty(M, D, dtype=torch.float32, device=x.device)
+    check(load().stad_layernorm(ptr(x), ptr(_req(g, torch.float32, "g")), ptr(_req(b, torch.float32, "b")), ptr(y), M,
+                                D, eps, stream_ptr()), "stad_layernorm")
+    return y
+
+
+def pool_norm_head(x, g, b, w_head, b_head, eps, want_probs=False):
+    init(x.device)
+    _req(x, torch.bfloat16, "x")
+    B, N, D = x.shape
+    Cn = w_head.shape[0]
+    logits = torch.empty(B, Cn, dtype=torch.float32, device=x.device)
+    probs = torch.empty(B, Cn, dtype=torch.float32, device=x.device) if want_probs else None
+    scratch = torch.empty(B * 16 * D, dtype=torch.float32, device=x.device)
+    check(load().stad_pool_norm_head(ptr(x), ptr(g), ptr(b), ptr(_req(w_head, torch.float32, "w_head")), ptr(b_head),
+                                     ptr(logits), ptr(probs), ptr(scratch), B, N, D, Cn, eps, stream_ptr()),
+          "stad_pool_norm_head")
+    return (logits, probs) if want_probs else logits
+
+
+def ln_gemm(x, stats, w, bias, colsum, gelu=False, out=None):
+    init(x.device)
+    _req(x, torch.bfloat16, "x")
+    _req(w, torch.bfloat16, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"ln_gemm: x is [{M},{K}] but w is {tuple(w.shape)}")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=x.device)
+    check(load().stad_ln_gemm(ptr(x), ptr(_req(stats, torch.float32, "stats")), ptr(w), ptr(bias), ptr(colsum),
+                              STAD_EPI_BIAS_GELU if gelu else STAD_EPI_BIAS, ptr(out), M, N, K, stream_ptr()),
+          "stad_ln_gemm")
+    return out
+
+
+def gemm_bias_residual(a, w, bias=None, residual=None, out=None):
+    init(a.device)
+    _req(a, torch.bfloat16, "a")
+    _req(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"gemm: a is [{M},{K}] but w is {tuple(w.shape)}")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    check(load().stad_gemm_bias_residual(ptr(a), ptr(w), ptr(bias), ptr(residual), ptr(out), M, N, K, stream_ptr()),
+          "stad_gemm_bias_residual")
+    return out
+
+
+def attention(qkv, scale=None, out=None):
+    """qkv [B, S, 3, H, 64] bf16 -> [B, S, H*64] bf16 (the tensors of FlashAttention.forward, fac:26-51)."""
+    init(qkv.device)
+    _req(qkv, torch.bfloat16, "qkv")
+    if qkv.dim() != 5 or qkv.shape[2] != 3 or qkv.shape[4] != 64:
+        raise ValueError(f"attention: qkv must be [B, S, 3, H, 64], got {tuple(qkv.shape)}")
+    B, S, _, H, Dh = qkv.shape
+    if scale is None:
+        scale = Dh ** -0.5
+    if out is None:
+        out = torch.empty(B, S, H * Dh, dtype=torch.bfloat16, device=qkv.device)
+    check(load().stad_attention(ptr(qkv), ptr(out), B, H, S, float(scale), stream_ptr()), "stad_attention")
+    return out
+
+
+def make_dims(img_h=224, img_w=224, patch=16, tubelet=2, frames=16, in_chans=3, dim=768, depth=12, heads=12,
+              hidden=3072, num_classes=2):
+    return StadDims(img_h, img_w, patch, tubelet, frames, in_chans, dim, depth, heads, hidden, num_classes)
+
+
+def make_input(data, mode=STAD_IN_CLIPS, n_frames=0, start=0, stride=1):
+    return StadInput(data.data_ptr(), mode, n_frames, start, stride)
+
+
+def patch_embed(x, w, pos_bias, dims, B, n_tok, tok_idx=None, mode=STAD_IN_CLIPS, n_frames=0, start=0, stride=1):
+    """x: bf16 planes ([B,C,T,H,W] clips or [F,C,H,W] frames) -> [B*n_tok, D] bf16."""
+    init(x.device)
+    _req(x, torch.bfloat16, "x")
+    _req(w, torch.bfloat16, "w")
+    _req(pos_bias, torch.float32, "pos_bias")
+    D = w.shape[0]
+    out = torch.empty(B * n_tok, D, dtype=torch.bfloat16, device=x.device)
+    gather = None
+    if tok_idx is not None:
+        _req(tok_idx, torch.int32, "tok_idx")
+        gather = torch.empty(B * n_tok, w.shape[1], dtype=torch.bfloat16, device=x.device)
+    inp = make_input(x, mode, n_frames, start, stride)
+    check(load().stad_patch_embed(C.byref(inp), ptr(w), ptr(pos_bias), ptr(tok_idx), ptr(out), ptr(gather),
+                                  C.byref(dims), B, n_tok, stream_ptr()), "stad_patch_embed")
+    return out

@@ -1,0 +1,309 @@
+// extern "C" surface of libstad.so (declared in include/stad.h) and the host-side sequencing of one forward.
+#include <mutex>
+
+#include "kernels.h"
+
+namespace stad {
+
+namespace {
+
+std::mutex g_init_mutex;
+bool g_inited = false;
+
+inline cudaStream_t as_stream(stad_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int check_dims(const stad_dims* d) {
+  STAD_CHECK_ARG(d != nullptr, "dims is NULL");
+  STAD_CHECK_ARG(d->patch == 16, "patch size %d unsupported (every reference factory uses 16, mf:338-398)", d->patch);
+  STAD_CHECK_ARG(d->tubelet >= 1 && d->frames % d->tubelet == 0, "frames=%d not divisible by tubelet=%d", d->frames,
+                 d->tubelet);
+  STAD_CHECK_ARG(d->img_h % 16 == 0 && d->img_w % 16 == 0 && d->img_h > 0 && d->img_w > 0,
+                 "image %dx%d is not a multiple of the patch size", d->img_h, d->img_w);
+  STAD_CHECK_ARG(d->img_w / 16 <= 128, "image width %d too large for one M-tile", d->img_w);
+  STAD_CHECK_ARG(d->in_chans >= 1, "in_chans=%d", d->in_chans);
+  STAD_CHECK_ARG(d->dim > 0 && d->dim % 64 == 0, "embed dim %d must be a multiple of 64", d->dim);
+  return STAD_OK;
+}
+
+int make_geom(const stad_dims* d, const stad_input* in, int B, PatchGeom* pg) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  STAD_CHECK_ARG(in != nullptr && in->data != nullptr, "input is NULL");
+  pg->Tp = d->frames / d->tubelet;
+  pg->Hp = d->img_h / 16;
+  pg->Wp = d->img_w / 16;
+  const int max_rows = 128 / pg->Wp;                       // h' rows that fit one 128-row MMA tile
+  pg->h_tiles = ceil_div(pg->Hp, max_rows);
+  pg->hp_tile = ceil_div(pg->Hp, pg->h_tiles);             // balanced split (224px: 7 + 7)
+  pg->C = d->in_chans;
+  pg->T = d->frames;
+  pg->tubelet = d->tubelet;
+  pg->img_h = d->img_h;
+  pg->img_w = d->img_w;
+  pg->mode = in->mode;
+  pg->start = in->start;
+  pg->stride = in->stride;
+  if (in->mode == STAD_IN_CLIPS) {
+    pg->n_planes = B * d->in_chans * d->frames;
+    pg->start = 0;
+    pg->stride = 0;
+  } else if (in->mode == STAD_IN_FRAMES) {
+    STAD_CHECK_ARG(in->stride >= 1 && in->start >= 0, "frames input: start=%d stride=%d", in->start, in->stride);
+    STAD_CHECK_ARG(in->start + (B - 1) * in->stride + d->frames <= in->n_frames,
+                   "frames input: clip %d needs frame %d but only %d frames are resident", B - 1,
+                   in->start + (B - 1) * in->stride + d->frames - 1, in->n_frames);
+    pg->n_planes = in->n_frames * d->in_chans;
+  } else {
+    return fail(STAD_E_SHAPE, "unknown input mode %d", in->mode);
+  }
+  return STAD_OK;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+struct Workspace {
+  bf16* x;       // [M, D]   residual stream
+  float2* stats; // [M]
+  bf16* qkv;     // [M, 3D]
+  bf16* attn;    // [M, D]   (directly after qkv)
+  bf16* hidden;  // [M, 4D]  aliases qkv+attn: qkv/attn are dead once proj has run
+  float* pool;   // [B, 16, D]
+  bf16* gather;  // [M, K]   visible-token im2col (masked path only)
+  size_t bytes;
+};
+
+Workspace carve(const stad_dims* d, int B, int n_tok, void* base) {
+  Workspace w;
+  const size_t M = static_cast<size_t>(B) * n_tok;
+  const size_t D = d->dim;
+  const size_t K = static_cast<size_t>(d->in_chans) * d->tubelet * 256;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += align256(bytes);
+    return o;
+  };
+  uint8_t* p = static_cast<uint8_t*>(base);
+  const size_t o_x = take(M * D * 2);
+  const size_t o_stats = take(M * sizeof(float2));
+  const size_t hid = static_cast<size_t>(d->hidden) > 4 * D ? d->hidden : 4 * D;
+  const size_t o_big = take(M * hid * 2);
+  const size_t o_pool = take(static_cast<size_t>(B) * 16 * D * sizeof(float));
+  const int n_full = (d->frames / d->tubelet) * (d->img_h / 16) * (d->img_w / 16);
+  const size_t o_gather = take(n_tok == n_full ? 0 : M * K * 2);  // im2col scratch only on the visible-token path
+  w.x = reinterpret_cast<bf16*>(p + o_x);
+  w.stats = reinterpret_cast<float2*>(p + o_stats);
+  w.qkv = reinterpret_cast<bf16*>(p + o_big);
+  w.attn = w.qkv + M * 3 * D;
+  w.hidden = w.qkv;
+  w.pool = reinterpret_cast<float*>(p + o_pool);
+  w.gather = reinterpret_cast<bf16*>(p + o_gather);
+  w.bytes = off;
+  return w;
+}
+
+int patch_embed_impl(const stad_input* in, const void* w, const float* pos_bias, const int32_t* tok_idx, void* out,
+                     void* gather, const stad_dims* d, int B, int n_tok, cudaStream_t stream, int* launches) {
+  PatchGeom pg;
+  int rc = make_geom(d, in, B, &pg);
+  if (rc) return rc;
+  const int N_full = pg.Tp * pg.Hp * pg.Wp;
+  const int K = d->in_chans * d->tubelet * 256;
+  GemmArgs g;
+  g.w = static_cast<const bf16*>(w);
+  g.N = d->dim;
+  g.K = K;
+  g.epi = EPI_POS;
+  g.pos = pos_bias;
+  g.out = static_cast<bf16*>(out);
+  if (tok_idx == nullptr) STAD_CHECK_ARG(n_tok == N_full, "patch_embed: n_tok=%d but the clip has %d tokens", n_tok, N_full);
+  // n_tok == N_full with an index list: every token survives, so the list is the identity (mp:98 keeps row-major order)
+  if (n_tok == N_full) {
+    g.a = static_cast<const bf16*>(in->data);
+    g.M = B * N_full;
+    g.pos_rows = N_full;
+    g.patch = &pg;
+    if ((rc = launch_gemm(g, stream))) return rc;
+    *launches += 1;
+  } else {
+    STAD_CHECK_ARG(n_tok >= 1 && n_tok <= N_full, "patch_embed: n_tok=%d out of range", n_tok);
+    STAD_CHECK_ARG(gather != nullptr, "patch_embed: visible-token mode needs gather scratch");
+    if ((rc = launch_gather_patches(static_cast<const bf16*>(in->data), pg, tok_idx, static_cast<bf16*>(gather), B,
+                                    n_tok, stream)))
+      return rc;
+    g.a = static_cast<const bf16*>(gather);
+    g.M = B * n_tok;
+    g.tok_idx = tok_idx;
+    g.pos_rows = N_full;
+    if ((rc = launch_gemm(g, stream))) return rc;
+    *launches += 2;
+  }
+  return STAD_OK;
+}
+
+}  // namespace
+}  // namespace stad
+
+using namespace stad;
+
+extern "C" {
+
+int stad_abi_version(void) { return STAD_ABI_VERSION; }
+
+const char* stad_last_error(void) { return last_error(); }
+
+int stad_init(int device) {
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  int count = 0;
+  STAD_CUDA_OK(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(STAD_E_SHAPE, "stad_init: device %d out of range (%d visible)", device, count);
+  int major = 0, minor = 0;
+  STAD_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  STAD_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  if (major != 10)
+    return fail(STAD_E_ARCH, "stad_init: device %d is sm_%d%d; libstad is built for sm_100a only and has no other path",
+                device, major, minor);
+  STAD_CUDA_OK(cudaSetDevice(device));
+  if (g_inited) return STAD_OK;
+  int rc;
+  if ((rc = gemm_init())) return rc;
+  if ((rc = attention_init())) return rc;
+  g_inited = true;
+  return STAD_OK;
+}
+
+int stad_cast_f32_bf16(const float* x, void* y, size_t n, stad_stream_t stream) {
+  return launch_cast_f32_bf16(x, static_cast<bf16*>(y), n, as_stream(stream));
+}
+
+int stad_row_stats(const void* x, float* stats, int M, int D, float eps, stad_stream_t stream) {
+  return launch_row_stats(static_cast<const bf16*>(x), reinterpret_cast<float2*>(stats), M, D, eps, as_stream(stream));
+}
+
+int stad_layernorm(const void* x, const float* g, const float* b, float* y, int M, int D, float eps,
+                   stad_stream_t stream) {
+  return launch_layernorm(static_cast<const bf16*>(x), g, b, y, M, D, eps, as_stream(stream));
+}
+
+int stad_pool_norm_head(const void* x, const float* g, const float* b, const float* w_head, const float* b_head,
+                        float* logits, float* probs, float* scratch, int B, int N, int D, int C, float eps,
+                        stad_stream_t stream) {
+  return launch_pool_norm_head(static_cast<const bf16*>(x), g, b, w_head, b_head, logits, probs, scratch, B, N, D, C,
+                               eps, as_stream(stream));
+}
+
+int stad_patch_embed(const stad_input* in, const void* w, const float* pos_bias, const int32_t* tok_idx, void* out,
+                     void* gather, const stad_dims* dims, int B, int n_tok, stad_stream_t stream) {
+  int launches = 0;
+  return patch_embed_impl(in, w, pos_bias, tok_idx, out, gather, dims, B, n_tok, as_stream(stream), &launches);
+}
+
+int stad_ln_gemm(const void* x, const float* stats, const void* w, const float* bias, const float* colsum,
+                 int epilogue, void* out, int M, int N, int K, stad_stream_t stream) {
+  STAD_CHECK_ARG(epilogue == STAD_EPI_BIAS || epilogue == STAD_EPI_BIAS_GELU, "ln_gemm: unknown epilogue %d", epilogue);
+  GemmArgs g;
+  g.a = static_cast<const bf16*>(x);
+  g.w = static_cast<const bf16*>(w);
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.epi = EPI_LN | (epilogue == STAD_EPI_BIAS_GELU ? EPI_GELU : 0);
+  g.bias = bias;
+  g.colsum = colsum;
+  g.stats = reinterpret_cast<const float2*>(stats);
+  g.out = static_cast<bf16*>(out);
+  return launch_gemm(g, as_stream(stream));
+}
+
+int stad_gemm_bias_residual(const void* a, const void* w, const float* bias, const void* residual, void* out, int M,
+                            int N, int K, stad_stream_t stream) {
+  GemmArgs g;
+  g.a = static_cast<const bf16*>(a);
+  g.w = static_cast<const bf16*>(w);
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.epi = residual ? EPI_RESID : 0;
+  g.bias = bias;
+  g.residual = static_cast<const bf16*>(residual);
+  g.out = static_cast<bf16*>(out);
+  return launch_gemm(g, as_stream(stream));
+}
+
+int stad_attention(const void* qkv, void* out, int B, int H, int S, float scale, stad_stream_t stream) {
+  return launch_attention(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), B, H, S, scale, as_stream(stream));
+}
+
+size_t stad_workspace_bytes(const stad_dims* dims, int B, int n_tok) {
+  if (dims == nullptr || B <= 0 || n_tok <= 0) return 0;
+  return carve(dims, B, n_tok, nullptr).bytes;
+}
+
+int stad_vit_forward(const stad_model* m, const stad_input* in, const int32_t* tok_idx, int B, int n_tok, float* logits,
+                     float* probs, float* tokens_out, void* workspace, size_t workspace_bytes, stad_stream_t stream_) {
+  STAD_CHECK_ARG(m != nullptr && m->blocks != nullptr, "vit_forward: model is NULL");
+  STAD_CHECK_ARG(B > 0 && n_tok > 0, "vit_forward: B=%d n_tok=%d", B, n_tok);
+  const stad_dims* d = &m->dims;
+  int rc = check_dims(d);
+  if (rc) return rc;
+  STAD_CHECK_ARG(d->heads * 64 == d->dim, "vit_forward: head dim must be 64 (dim=%d heads=%d)", d->dim, d->heads);
+  STAD_CHECK_ARG(workspace != nullptr, "vit_forward: workspace is NULL");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(STAD_E_ALIGN, "vit_forward: workspace must be 256-byte aligned");
+  Workspace ws = carve(d, B, n_tok, workspace);
+  STAD_CHECK_ARG(ws.bytes <= workspace_bytes, "vit_forward: workspace too small (%zu < %zu bytes)", workspace_bytes,
+                 ws.bytes);
+  const bool classifier = d->num_classes > 0;
+  if (classifier) STAD_CHECK_ARG(logits && m->w_head && m->b_head, "vit_forward: classifier path needs logits/head");
+  else STAD_CHECK_ARG(tokens_out, "vit_forward: encoder path needs tokens_out");
+  STAD_CHECK_ARG(m->norm_g && m->norm_b, "vit_forward: final norm weights missing");
+
+  cudaStream_t stream = as_stream(stream_);
+  const int M = B * n_tok;
+  const int D = d->dim;
+  int launches = 0;
+
+  // PatchEmbed + position table (mf:309-313 / mp:93-98)
+  if ((rc = patch_embed_impl(in, m->w_patch, m->pos_bias, tok_idx, ws.x, ws.gather, d, B, n_tok, stream, &launches)))
+    return rc;
+
+  for (int l = 0; l < d->depth; ++l) {
+    const stad_block& blk = m->blocks[l];
+    // x = x + proj(attn(norm1(x)))                                     (mf:161)
+    if ((rc = launch_row_stats(ws.x, ws.stats, M, D, m->eps, stream))) return rc;
+    GemmArgs q;
+    q.a = ws.x; q.w = static_cast<const bf16*>(blk.w_qkv); q.M = M; q.N = 3 * D; q.K = D;
+    q.epi = EPI_LN; q.bias = blk.b_qkv; q.colsum = blk.cs_qkv; q.stats = ws.stats; q.out = ws.qkv;
+    if ((rc = launch_gemm(q, stream))) return rc;
+    if ((rc = launch_attention(ws.qkv, ws.attn, B, d->heads, n_tok, m->attn_scale, stream))) return rc;
+    GemmArgs pr;
+    pr.a = ws.attn; pr.w = static_cast<const bf16*>(blk.w_proj); pr.M = M; pr.N = D; pr.K = D;
+    pr.epi = EPI_RESID; pr.bias = blk.b_proj; pr.residual = ws.x; pr.out = ws.x;
+    if ((rc = launch_gemm(pr, stream))) return rc;
+    // x = x + fc2(gelu(fc1(norm2(x))))                                 (mf:162)
+    if ((rc = launch_row_stats(ws.x, ws.stats, M, D, m->eps, stream))) return rc;
+    GemmArgs f1;
+    f1.a = ws.x; f1.w = static_cast<const bf16*>(blk.w_fc1); f1.M = M; f1.N = d->hidden; f1.K = D;
+    f1.epi = EPI_LN | EPI_GELU; f1.bias = blk.b_fc1; f1.colsum = blk.cs_fc1; f1.stats = ws.stats; f1.out = ws.hidden;
+    if ((rc = launch_gemm(f1, stream))) return rc;
+    GemmArgs f2;
+    f2.a = ws.hidden; f2.w = static_cast<const bf16*>(blk.w_fc2); f2.M = M; f2.N = D; f2.K = d->hidden;
+    f2.epi = EPI_RESID; f2.bias = blk.b_fc2; f2.residual = ws.x; f2.out = ws.x;
+    if ((rc = launch_gemm(f2, stream))) return rc;
+    launches += 7;
+  }
+
+  if (classifier) {
+    // norm = Identity; mean over tokens; fc_norm; head                (mf:323-326, mf:334)
+    if ((rc = launch_pool_norm_head(ws.x, m->norm_g, m->norm_b, m->w_head, m->b_head, logits, probs, ws.pool, B, n_tok,
+                                    D, d->num_classes, m->eps, stream)))
+      return rc;
+    launches += 2;
+  } else {
+    // encoder: norm over every visible token, head = Identity         (mp:107, mp:112)
+    if ((rc = launch_layernorm(ws.x, m->norm_g, m->norm_b, tokens_out, M, D, m->eps, stream))) return rc;
+    launches += 1;
+  }
+  return launches;
+}
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+// Host-side plumbing shared by every translation unit of libstad.so: error reporting, tensor-map
+// encoding (driver entry point fetched through the runtime so the library links only libcudart).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/stad.h"
+
+namespace stad {
+
+typedef __nv_bfloat16 bf16;
+
+// Sets the thread-local message returned by stad_last_error() and returns `code`.
+int fail(int code, const char* fmt, ...);
+const char* last_error();
+
+#define STAD_CHECK_ARG(cond, ...)                        \
+  do {                                                   \
+    if (!(cond)) return ::stad::fail(STAD_E_SHAPE, __VA_ARGS__); \
+  } while (0)
+
+#define STAD_CUDA_OK(expr)                                                                                \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess)                                                                                \
+      return ::stad::fail(STAD_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// Launch-time check: catches bad configuration (too much smem, ...) without synchronising.
+#define STAD_LAUNCH_OK(what)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = cudaGetLastError();                                                          \
+    if (_e != cudaSuccess) return ::stad::fail(STAD_E_CUDA, "%s launch: %s", what, cudaGetErrorString(_e)); \
+  } while (0)
+
+int sm_count();  // SMs of the current device (cached)
+
+// rank-N bf16 tensor map with 128-byte swizzle. dims/strides innermost-first; strides in BYTES for dims 1..rank-1.
+int make_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace stad

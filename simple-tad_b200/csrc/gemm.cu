@@ -1,0 +1,452 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  out[M,N] = epilogue(A[M,K] . W[N,K]^T)
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      : MMA issuer     (one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128 x N=BN x K=16)
+//                 + TMEM owner   (2 accumulator stages so the epilogue of tile i overlaps the mainloop of tile i+1)
+//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> registers -> bias / LN-fold / GELU / residual / pos -> bf16 -> HBM)
+//
+// Replaces every nn.Linear / F.linear on the reference path (modeling_finetune.py:48,52,92,104,119,128) and, in
+// patch mode, the Conv3d of PatchEmbed (modeling_finetune.py:181-190): the A operand is then fetched with a 5-D tensor
+// map straight out of the [.., H, W] clip planes (im2col-free), k order (c, dt, dh, dw) = Conv3d weight order.
+//
+// Roofline: dense BF16 tensor. Algorithmic FLOPs = 2 M N K; HBM bytes = 2 (M K + N K + M N) (+ 2 M N residual).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace stad {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (2 + kEpiWarps);
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 256 ? 4 : BN == 192 ? 5 : BN == 128 ? 6 : 8;
+  static constexpr int ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator stage
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1024B alignment
+};
+
+struct KArgs {
+  int M, N, K;
+  int m_tiles, n_tiles;
+  const float* bias;
+  const float* colsum;
+  const float2* stats;
+  const bf16* residual;
+  const float* pos;
+  const int32_t* tok_idx;
+  int pos_rows;
+  bf16* out;
+  PatchGeom pg;
+};
+
+// Row bookkeeping of one M-tile: which output rows the 128 accumulator lanes map to.
+struct TileRows {
+  int row0;        // output row of lane 0
+  int valid_rows;  // lanes >= valid_rows are padding
+};
+
+template <bool kPatch>
+STAD_DEVICE TileRows tile_rows(const KArgs& p, int m_tile) {
+  TileRows t;
+  if constexpr (kPatch) {
+    const PatchGeom& g = p.pg;
+    const int hh = m_tile % g.h_tiles;
+    const int tp = (m_tile / g.h_tiles) % g.Tp;
+    const int b = m_tile / (g.h_tiles * g.Tp);
+    const int h0 = hh * g.hp_tile;
+    const int hrows = min(g.hp_tile, g.Hp - h0);
+    t.row0 = (b * g.Tp + tp) * g.Hp * g.Wp + h0 * g.Wp;
+    t.valid_rows = hrows * g.Wp;
+  } else {
+    t.row0 = m_tile * BM;
+    t.valid_rows = min(BM, p.M - t.row0);
+  }
+  return t;
+}
+
+template <int BN, int EPI, bool kPatch>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const KArgs p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle needs 1024-byte aligned tiles; align in the shared address space.
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_kb = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile % p.n_tiles;
+        int a_bytes = C::A_BYTES;
+        int pe_b = 0, pe_tp = 0, pe_h0 = 0;
+        if constexpr (kPatch) {
+          const PatchGeom& g = p.pg;
+          const int hh = m_tile % g.h_tiles;
+          pe_tp = (m_tile / g.h_tiles) % g.Tp;
+          pe_b = m_tile / (g.h_tiles * g.Tp);
+          pe_h0 = hh * g.hp_tile;
+          a_bytes = g.Wp * g.hp_tile * BK * 2;  // full box, out-of-range h' rows arrive as zeros
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], a_bytes + C::B_BYTES);
+          if constexpr (kPatch) {
+            // k chunk kb = 64 consecutive k = (c, dt, dh0..dh0+3, dw 0..15)
+            const PatchGeom& g = p.pg;
+            const int c = kb / (g.tubelet * 4);
+            const int dt = (kb >> 2) % g.tubelet;
+            const int dh0 = (kb & 3) * 4;
+            const int t = pe_tp * g.tubelet + dt;
+            const int plane = g.mode == STAD_IN_CLIPS ? (pe_b * g.C + c) * g.T + t
+                                                      : (g.start + pe_b * g.stride + t) * g.C + c;
+            tma_load_5d(sa, &tmap_a, &full_bar[stage], 0, dh0, 0, pe_h0, plane);
+          } else {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_tile * BM);
+          }
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_tile * BN);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;            // 0..7
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int half = ew >> 2;           // which half of the BN columns
+    constexpr int COLS = BN / 2;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile % p.n_tiles;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const TileRows tr = tile_rows<kPatch>(p, m_tile);
+      const int r = quarter * 32 + lane;
+      const bool row_ok = r < tr.valid_rows;
+      const int row = tr.row0 + r;
+
+      float mean = 0.f, rstd = 1.f;
+      if constexpr (EPI & EPI_LN) {
+        if (row_ok) {
+          const float2 st = __ldg(&p.stats[row]);
+          mean = st.x;
+          rstd = st.y;
+        }
+      }
+      const float* pos_row = nullptr;
+      if constexpr (EPI & EPI_POS) {
+        if (row_ok) {
+          const int pr = p.tok_idx ? __ldg(&p.tok_idx[row]) : row % p.pos_rows;
+          pos_row = p.pos + static_cast<size_t>(pr) * p.N;
+        }
+      }
+
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::ACC_STRIDE + half * COLS;
+#pragma unroll 1
+      for (int c0 = 0; c0 < COLS; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        tmem_ld_wait();
+        const int n0 = n_tile * BN + half * COLS + c0;
+        if (n0 < p.N) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if constexpr (EPI & EPI_LN) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 cs = __ldg(reinterpret_cast<const float4*>(p.colsum + n0 + j));
+              f[j + 0] = rstd * fmaf(-mean, cs.x, f[j + 0]);
+              f[j + 1] = rstd * fmaf(-mean, cs.y, f[j + 1]);
+              f[j + 2] = rstd * fmaf(-mean, cs.z, f[j + 2]);
+              f[j + 3] = rstd * fmaf(-mean, cs.w, f[j + 3]);
+            }
+          }
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              f[j + 0] += bv.x;
+              f[j + 1] += bv.y;
+              f[j + 2] += bv.z;
+              f[j + 3] += bv.w;
+            }
+          }
+          if constexpr (EPI & EPI_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          }
+          if (row_ok) {
+            if constexpr (EPI & EPI_POS) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 pv = __ldg(reinterpret_cast<const float4*>(pos_row + n0 + j));
+                f[j + 0] += pv.x;
+                f[j + 1] += pv.y;
+                f[j + 2] += pv.z;
+                f[j + 3] += pv.w;
+              }
+            }
+            const size_t off = static_cast<size_t>(row) * p.N + n0;
+            if constexpr (EPI & EPI_RESID) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 rv = rp[q];
+                f[q * 8 + 0] += bf16_lo(rv.x);
+                f[q * 8 + 1] += bf16_hi(rv.x);
+                f[q * 8 + 2] += bf16_lo(rv.y);
+                f[q * 8 + 3] += bf16_hi(rv.y);
+                f[q * 8 + 4] += bf16_lo(rv.z);
+                f[q * 8 + 5] += bf16_hi(rv.z);
+                f[q * 8 + 6] += bf16_lo(rv.w);
+                f[q * 8 + 7] += bf16_hi(rv.w);
+              }
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack_bf16(f[q * 8 + 0], f[q * 8 + 1]);
+              o.y = pack_bf16(f[q * 8 + 2], f[q * 8 + 3]);
+              o.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]);
+              o.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
+              op[q] = o;
+            }
+          }
+        }
+      }
+      // accumulator stage drained: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int EPI, bool kPatch>
+int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& ka, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  const int tiles = ka.m_tiles * ka.n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_kernel<BN, EPI, kPatch><<<grid, kThreads, C::SMEM_BYTES, stream>>>(ta, tb, ka);
+  STAD_LAUNCH_OK("gemm_kernel");
+  return STAD_OK;
+}
+
+template <int BN, int EPI, bool kPatch>
+int set_smem() {
+  STAD_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, kPatch>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg<BN>::SMEM_BYTES));
+  return STAD_OK;
+}
+
+template <int EPI, bool kPatch>
+int set_smem_all_bn() {
+  int rc;
+  if ((rc = set_smem<64, EPI, kPatch>())) return rc;
+  if ((rc = set_smem<128, EPI, kPatch>())) return rc;
+  if ((rc = set_smem<192, EPI, kPatch>())) return rc;
+  if ((rc = set_smem<256, EPI, kPatch>())) return rc;
+  return STAD_OK;
+}
+
+template <int EPI, bool kPatch>
+int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& ka, cudaStream_t stream) {
+  switch (bn) {
+    case 64: return launch_one<64, EPI, kPatch>(ta, tb, ka, stream);
+    case 128: return launch_one<128, EPI, kPatch>(ta, tb, ka, stream);
+    case 192: return launch_one<192, EPI, kPatch>(ta, tb, ka, stream);
+    case 256: return launch_one<256, EPI, kPatch>(ta, tb, ka, stream);
+  }
+  return fail(STAD_E_SHAPE, "gemm: no tile width for N");
+}
+
+// Widest BN that divides N and still yields at least one full wave of tiles; else the narrowest that divides N.
+int pick_bn(int m_tiles, int N) {
+  const int cand[4] = {256, 192, 128, 64};
+  int narrow = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (N % cand[i] != 0) continue;
+    narrow = cand[i];
+    if (m_tiles * (N / cand[i]) >= sm_count()) return cand[i];
+  }
+  return narrow;
+}
+
+}  // namespace
+
+int gemm_init() {
+  int rc;
+  if ((rc = set_smem_all_bn<0, false>())) return rc;
+  if ((rc = set_smem_all_bn<EPI_LN, false>())) return rc;
+  if ((rc = set_smem_all_bn<EPI_LN | EPI_GELU, false>())) return rc;
+  if ((rc = set_smem_all_bn<EPI_RESID, false>())) return rc;
+  if ((rc = set_smem_all_bn<EPI_POS, false>())) return rc;
+  if ((rc = set_smem_all_bn<EPI_POS, true>())) return rc;
+  return STAD_OK;
+}
+
+int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
+  STAD_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  STAD_CHECK_ARG(g.K % BK == 0, "gemm: K=%d must be a multiple of %d", g.K, BK);
+  STAD_CHECK_ARG(g.N % 64 == 0, "gemm: N=%d must be a multiple of 64", g.N);
+  if ((reinterpret_cast<uintptr_t>(g.a) | reinterpret_cast<uintptr_t>(g.w) | reinterpret_cast<uintptr_t>(g.out) |
+       reinterpret_cast<uintptr_t>(g.residual) | reinterpret_cast<uintptr_t>(g.bias) |
+       reinterpret_cast<uintptr_t>(g.colsum) | reinterpret_cast<uintptr_t>(g.pos)) & 15)
+    return fail(STAD_E_ALIGN, "gemm: all operands must be 16-byte aligned");
+  if (g.epi & EPI_LN) STAD_CHECK_ARG(g.stats && g.colsum, "gemm: LN epilogue needs stats and colsum");
+  if (g.epi & EPI_RESID) STAD_CHECK_ARG(g.residual, "gemm: residual epilogue needs a residual");
+  if (g.epi & EPI_POS) STAD_CHECK_ARG(g.pos && (g.tok_idx || g.pos_rows > 0), "gemm: pos epilogue needs a table");
+
+  KArgs ka{};
+  ka.M = g.M;
+  ka.N = g.N;
+  ka.K = g.K;
+  ka.bias = g.bias;
+  ka.colsum = g.colsum;
+  ka.stats = g.stats;
+  ka.residual = g.residual;
+  ka.pos = g.pos;
+  ka.tok_idx = g.tok_idx;
+  ka.pos_rows = g.pos_rows;
+  ka.out = g.out;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (g.patch) {
+    const PatchGeom& pg = *g.patch;
+    ka.pg = pg;
+    ka.m_tiles = (g.M / (pg.Tp * pg.Hp * pg.Wp)) * pg.Tp * pg.h_tiles;
+    // dims innermost-first: dw(16) dh(16) w'(Wp) h'(Hp) plane
+    const uint64_t dims[5] = {16, 16, (uint64_t)pg.Wp, (uint64_t)pg.Hp, (uint64_t)pg.n_planes};
+    const uint64_t strides[4] = {(uint64_t)pg.img_w * 2, 32, (uint64_t)pg.img_w * 32,
+                                 (uint64_t)pg.img_h * pg.img_w * 2};
+    const uint32_t box[5] = {16, 4, (uint32_t)pg.Wp, (uint32_t)pg.hp_tile, 1};
+    if ((rc = make_tmap_bf16(&ta, g.a, 5, dims, strides, box))) return rc;
+  } else {
+    ka.m_tiles = ceil_div(g.M, BM);
+    const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.M};
+    const uint64_t strides[1] = {(uint64_t)g.K * 2};
+    const uint32_t box[2] = {BK, BM};
+    if ((rc = make_tmap_bf16(&ta, g.a, 2, dims, strides, box))) return rc;
+  }
+  const int bn = pick_bn(ka.m_tiles, g.N);
+  ka.n_tiles = g.N / bn;
+  {
+    const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
+    const uint64_t strides[1] = {(uint64_t)g.K * 2};
+    const uint32_t box[2] = {BK, (uint32_t)bn};
+    if ((rc = make_tmap_bf16(&tb, g.w, 2, dims, strides, box))) return rc;
+  }
+
+  if (g.patch) {
+    STAD_CHECK_ARG(g.epi == EPI_POS, "gemm: patch mode supports only the pos epilogue");
+    return dispatch_bn<EPI_POS, true>(bn, ta, tb, ka, stream);
+  }
+  switch (g.epi) {
+    case 0: return dispatch_bn<0, false>(bn, ta, tb, ka, stream);
+    case EPI_LN: return dispatch_bn<EPI_LN, false>(bn, ta, tb, ka, stream);
+    case EPI_LN | EPI_GELU: return dispatch_bn<EPI_LN | EPI_GELU, false>(bn, ta, tb, ka, stream);
+    case EPI_RESID: return dispatch_bn<EPI_RESID, false>(bn, ta, tb, ka, stream);
+    case EPI_POS: return dispatch_bn<EPI_POS, false>(bn, ta, tb, ka, stream);
+  }
+  return fail(STAD_E_SHAPE, "gemm: unsupported epilogue combination %d", g.epi);
+}
+
+}  // namespace stad

@@ -1,0 +1,53 @@
+// Internal launch interface between api.cu and the kernel translation units.
+#pragma once
+#include "common.h"
+
+namespace stad {
+
+// Geometry of the tubelet patch grid and of where the clips live (see stad_input in include/stad.h).
+struct PatchGeom {
+  int Tp, Hp, Wp;   // token grid: 8 x 14 x 14
+  int hp_tile;      // h' rows per M-tile (Wp * hp_tile <= 128)
+  int h_tiles;      // M-tiles per t' slot
+  int C, T, tubelet;
+  int img_h, img_w;
+  int mode, start, stride;  // STAD_IN_CLIPS / STAD_IN_FRAMES
+  int n_planes;             // extent of the plane dimension of the input tensor map
+};
+
+enum : int { EPI_LN = 1, EPI_GELU = 2, EPI_RESID = 4, EPI_POS = 8 };
+
+struct GemmArgs {
+  const bf16* a = nullptr;  // [M, K] (plain) or the bf16 plane tensor (patch mode)
+  const bf16* w = nullptr;  // [N, K]
+  int M = 0, N = 0, K = 0;
+  int epi = 0;                       // EPI_* bits
+  const float* bias = nullptr;       // [N] or null
+  const float* colsum = nullptr;     // [N]   (EPI_LN)
+  const float2* stats = nullptr;     // [M]   (EPI_LN) (mean, rstd)
+  const bf16* residual = nullptr;    // [M,N] (EPI_RESID)
+  const float* pos = nullptr;        // [pos_rows, N] (EPI_POS)
+  const int32_t* tok_idx = nullptr;  // [M] row -> pos row, or null: pos row = m % pos_rows
+  int pos_rows = 0;
+  bf16* out = nullptr;               // [M, N]
+  const PatchGeom* patch = nullptr;  // non-null: A is gathered straight from the clip planes by 5-D TMA
+};
+
+int launch_gemm(const GemmArgs& g, cudaStream_t stream);
+int gemm_init();  // raise dynamic smem limits
+
+int launch_attention(const bf16* qkv, bf16* out, int B, int H, int S, float scale, cudaStream_t stream);
+int attention_init();
+
+int launch_cast_f32_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream);
+int launch_row_stats(const bf16* x, float2* stats, int M, int D, float eps, cudaStream_t stream);
+int launch_layernorm(const bf16* x, const float* g, const float* b, float* y, int M, int D, float eps,
+                     cudaStream_t stream);
+int launch_pool_norm_head(const bf16* x, const float* g, const float* b, const float* w_head, const float* b_head,
+                          float* logits, float* probs, float* scratch, int B, int N, int D, int C, float eps,
+                          cudaStream_t stream);
+// visible-token im2col: out[B*n_tok, K] bf16 rows (c, dt, dh, dw) of the listed tokens
+int launch_gather_patches(const bf16* planes, const PatchGeom& pg, const int32_t* tok_idx, bf16* out, int B,
+                          int n_tok, cudaStream_t stream);
+
+}  // namespace stad

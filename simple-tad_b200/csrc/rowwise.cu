@@ -1,0 +1,320 @@
+// HBM-bound row kernels: input cast, LayerNorm statistics, final LayerNorm, mean-pool + fc_norm + head, and the
+// visible-token patch gather.  Each is a single pass over its input with 16-byte vector accesses; the roofline
+// that bounds them is HBM bandwidth (algorithmic bytes are stated per kernel).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace stad {
+
+namespace {
+
+constexpr int kMaxChunks = 8;  // 8 x (32 lanes x 8 bf16) = D <= 2048
+
+STAD_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+STAD_DEVICE void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x);
+  f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z);
+  f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 -> bf16.  Bytes: 4n read + 2n written.
+__global__ void cast_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n8, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+    uint4 o;
+    o.x = pack_bf16(a.x, a.y);
+    o.y = pack_bf16(a.z, a.w);
+    o.z = pack_bf16(b.x, b.y);
+    o.w = pack_bf16(b.z, b.w);
+    reinterpret_cast<uint4*>(y)[i] = o;
+  }
+  // tail (n not a multiple of 8)
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const size_t i = (n8 << 3) + threadIdx.x;
+    y[i] = __float2bfloat16_rn(x[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One warp per row; the row stays in registers between the mean pass and the variance pass (two-pass variance,
+// like ATen's layer_norm, so no E[x^2]-mean^2 cancellation).  Bytes: 2 M D read (+ 8 M or 4 M D written).
+template <bool kWriteNorm>
+__global__ void __launch_bounds__(256)
+row_norm_kernel(const bf16* __restrict__ x, float2* __restrict__ stats, const float* __restrict__ g,
+                const float* __restrict__ b, float* __restrict__ y, int M, int D, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int chunks = D >> 3;  // 16-byte chunks per row
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(warp) * D);
+  float v[kMaxChunks][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int idx = c * 32 + lane;
+    if (idx < chunks) {
+      unpack8(__ldg(xr + idx), v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[c][j];
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int idx = c * 32 + lane;
+    if (idx < chunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[c][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float var = warp_sum(q) / static_cast<float>(D);
+  const float rstd = rsqrtf(var + eps);
+  if constexpr (!kWriteNorm) {
+    if (lane == 0) stats[warp] = make_float2(mean, rstd);
+  } else {
+    float* yr = y + static_cast<size_t>(warp) * D;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int idx = c * 32 + lane;
+      if (idx < chunks) {
+        const int col = idx * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + col));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + col + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + col));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(b + col + 4));
+        float4 o0, o1;
+        o0.x = fmaf((v[c][0] - mean) * rstd, g0.x, b0.x);
+        o0.y = fmaf((v[c][1] - mean) * rstd, g0.y, b0.y);
+        o0.z = fmaf((v[c][2] - mean) * rstd, g0.z, b0.z);
+        o0.w = fmaf((v[c][3] - mean) * rstd, g0.w, b0.w);
+        o1.x = fmaf((v[c][4] - mean) * rstd, g1.x, b1.x);
+        o1.y = fmaf((v[c][5] - mean) * rstd, g1.y, b1.y);
+        o1.z = fmaf((v[c][6] - mean) * rstd, g1.z, b1.z);
+        o1.w = fmaf((v[c][7] - mean) * rstd, g1.w, b1.w);
+        reinterpret_cast<float4*>(yr + col)[0] = o0;
+        reinterpret_cast<float4*>(yr + col)[1] = o1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// mean-pool stage 1: grid (kPoolChunks, B); block sums its slice of the tokens for every column.
+// Bytes: 2 B N D read + 4 B kPoolChunks D written.  Deterministic (no atomics).
+constexpr int kPoolChunks = 16;
+
+__global__ void __launch_bounds__(256)
+pool_partial_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int N, int D) {
+  extern __shared__ float red[];  // [groups][D]
+  const int cpr = D >> 3;                 // 16-byte chunks per row
+  const int groups = blockDim.x / cpr;    // row groups working in parallel
+  const int grp = threadIdx.x / cpr;
+  const int ch = threadIdx.x % cpr;
+  const int b = blockIdx.y;
+  const int per = (N + kPoolChunks - 1) / kPoolChunks;
+  const int n0 = blockIdx.x * per;
+  const int n1 = min(N, n0 + per);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (grp < groups) {
+    const uint4* base = reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * N * D) + ch;
+    for (int n = n0 + grp; n < n1; n += groups) {
+      float f[8];
+      unpack8(__ldg(base + static_cast<size_t>(n) * cpr), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[grp * D + ch * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  float* out = partial + (static_cast<size_t>(b) * kPoolChunks + blockIdx.x) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f;
+    for (int gidx = 0; gidx < groups; ++gidx) s += red[gidx * D + c];
+    out[c] = s;
+  }
+}
+
+STAD_DEVICE float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) t += sh[i];
+  return t;
+}
+
+// stage 2: one block per clip: finish the mean, fc_norm (LayerNorm), head, optional softmax.
+__global__ void __launch_bounds__(256)
+pool_head_kernel(const float* __restrict__ partial, const float* __restrict__ g, const float* __restrict__ b,
+                 const float* __restrict__ w_head, const float* __restrict__ b_head, float* __restrict__ logits,
+                 float* __restrict__ probs, int N, int D, int C, float eps) {
+  extern __shared__ float sm[];  // [D] pooled / normalised vector, then [32] scratch, then [C] logits
+  float* vec = sm;
+  float* sh = sm + D;
+  float* lg = sh + 32;
+  const int bidx = blockIdx.x;
+  const float inv_n = 1.0f / static_cast<float>(N);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < kPoolChunks; ++k) t += partial[(static_cast<size_t>(bidx) * kPoolChunks + k) * D + c];
+    t *= inv_n;
+    vec[c] = t;
+    s += t;
+  }
+  const float mean = block_sum(s, sh) / static_cast<float>(D);
+  float q = 0.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float d = vec[c] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float var = block_sum(q, sh) / static_cast<float>(D);
+  const float rstd = rsqrtf(var + eps);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) vec[c] = fmaf((vec[c] - mean) * rstd, g[c], b[c]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int cls = warp; cls < C; cls += nw) {
+    float d = 0.f;
+    for (int c = lane; c < D; c += 32) d = fmaf(vec[c], w_head[static_cast<size_t>(cls) * D + c], d);
+    d = warp_sum(d);
+    if (lane == 0) {
+      d += b_head[cls];
+      lg[cls] = d;
+      logits[static_cast<size_t>(bidx) * C + cls] = d;
+    }
+  }
+  __syncthreads();
+  if (probs != nullptr && threadIdx.x == 0) {
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, lg[c]);
+    float den = 0.f;
+    for (int c = 0; c < C; ++c) den += expf(lg[c] - mx);
+    for (int c = 0; c < C; ++c) probs[static_cast<size_t>(bidx) * C + c] = expf(lg[c] - mx) / den;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// visible-token im2col (masked encoder, modeling_pretrain.py:93-98 restricted to the tokens that survive):
+// one thread moves 8 contiguous dw pixels (16 bytes).
+__global__ void __launch_bounds__(256)
+gather_patches_kernel(const bf16* __restrict__ planes, PatchGeom pg, const int32_t* __restrict__ tok_idx,
+                      bf16* __restrict__ out, int B, int n_tok, int K) {
+  const int k8 = K >> 3;
+  const size_t total = static_cast<size_t>(B) * n_tok * k8;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int kc = static_cast<int>(i % k8);
+  const size_t row = i / k8;
+  const int b = static_cast<int>(row / n_tok);
+  const int tok = __ldg(&tok_idx[row]);
+  const int wp = tok % pg.Wp;
+  const int hp = (tok / pg.Wp) % pg.Hp;
+  const int tp = tok / (pg.Wp * pg.Hp);
+  const int k = kc * 8;  // k = ((c*tubelet + dt)*16 + dh)*16 + dw
+  const int dw = k & 15;
+  const int dh = (k >> 4) & 15;
+  const int dt = (k >> 8) % pg.tubelet;
+  const int c = (k >> 8) / pg.tubelet;
+  const int t = tp * pg.tubelet + dt;
+  const int plane = pg.mode == STAD_IN_CLIPS ? (b * pg.C + c) * pg.T + t : (pg.start + b * pg.stride + t) * pg.C + c;
+  const size_t src = (static_cast<size_t>(plane) * pg.img_h + hp * 16 + dh) * pg.img_w + wp * 16 + dw;
+  reinterpret_cast<uint4*>(out)[i] = __ldg(reinterpret_cast<const uint4*>(planes + src));
+}
+
+}  // namespace
+
+int launch_cast_f32_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream) {
+  if (n == 0) return STAD_OK;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15)
+    return fail(STAD_E_ALIGN, "cast: pointers must be 16-byte aligned");
+  const size_t n8 = n >> 3;
+  const int threads = 256;
+  size_t blocks = (n8 + threads - 1) / threads;
+  const size_t cap = static_cast<size_t>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  cast_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x, y, n8, n);
+  STAD_LAUNCH_OK("cast_kernel");
+  return STAD_OK;
+}
+
+static int check_row_args(const void* x, int M, int D) {
+  STAD_CHECK_ARG(M > 0 && D > 0, "row kernel: empty input M=%d D=%d", M, D);
+  STAD_CHECK_ARG(D % 8 == 0 && D <= kMaxChunks * 256, "row kernel: D=%d must be a multiple of 8 and <= %d", D,
+                 kMaxChunks * 256);
+  if (reinterpret_cast<uintptr_t>(x) & 15) return fail(STAD_E_ALIGN, "row kernel: x must be 16-byte aligned");
+  return STAD_OK;
+}
+
+int launch_row_stats(const bf16* x, float2* stats, int M, int D, float eps, cudaStream_t stream) {
+  int rc = check_row_args(x, M, D);
+  if (rc) return rc;
+  const int rows_per_block = 8;
+  row_norm_kernel<false><<<ceil_div(M, rows_per_block), rows_per_block * 32, 0, stream>>>(x, stats, nullptr, nullptr,
+                                                                                         nullptr, M, D, eps);
+  STAD_LAUNCH_OK("row_stats");
+  return STAD_OK;
+}
+
+int launch_layernorm(const bf16* x, const float* g, const float* b, float* y, int M, int D, float eps,
+                     cudaStream_t stream) {
+  int rc = check_row_args(x, M, D);
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15)
+    return fail(STAD_E_ALIGN, "layernorm: g, b, y must be 16-byte aligned");
+  const int rows_per_block = 8;
+  row_norm_kernel<true><<<ceil_div(M, rows_per_block), rows_per_block * 32, 0, stream>>>(x, nullptr, g, b, y, M, D,
+                                                                                        eps);
+  STAD_LAUNCH_OK("layernorm");
+  return STAD_OK;
+}
+
+int launch_pool_norm_head(const bf16* x, const float* g, const float* b, const float* w_head, const float* b_head,
+                          float* logits, float* probs, float* scratch, int B, int N, int D, int C, float eps,
+                          cudaStream_t stream) {
+  STAD_CHECK_ARG(B > 0 && N > 0 && C > 0 && C <= 1024, "pool_norm_head: bad sizes B=%d N=%d C=%d", B, N, C);
+  STAD_CHECK_ARG(D % 8 == 0 && D >= 8 && D <= 2048, "pool_norm_head: D=%d must be a multiple of 8 and <= 2048", D);
+  if (reinterpret_cast<uintptr_t>(x) & 15) return fail(STAD_E_ALIGN, "pool_norm_head: x must be 16-byte aligned");
+  const int threads = 256;
+  const int groups = threads / (D >> 3);
+  STAD_CHECK_ARG(groups >= 1, "pool_norm_head: D too large for the pooling block");
+  const size_t smem1 = static_cast<size_t>(groups) * D * sizeof(float);
+  pool_partial_kernel<<<dim3(kPoolChunks, B), threads, smem1, stream>>>(x, scratch, N, D);
+  STAD_LAUNCH_OK("pool_partial");
+  const size_t smem2 = (static_cast<size_t>(D) + 32 + C) * sizeof(float);
+  pool_head_kernel<<<B, threads, smem2, stream>>>(scratch, g, b, w_head, b_head, logits, probs, N, D, C, eps);
+  STAD_LAUNCH_OK("pool_head");
+  return STAD_OK;
+}
+
+int launch_gather_patches(const bf16* planes, const PatchGeom& pg, const int32_t* tok_idx, bf16* out, int B,
+                          int n_tok, cudaStream_t stream) {
+  const int K = pg.C * pg.tubelet * 256;
+  if ((reinterpret_cast<uintptr_t>(planes) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return fail(STAD_E_ALIGN, "gather_patches: pointers must be 16-byte aligned");
+  const size_t total = static_cast<size_t>(B) * n_tok * (K >> 3);
+  const int threads = 256;
+  gather_patches_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
+      planes, pg, tok_idx, out, B, n_tok, K);
+  STAD_LAUNCH_OK("gather_patches");
+  return STAD_OK;
+}
+
+}  // namespace stad

@@ -1,0 +1,205 @@
+"""Per-kernel numerics checks: each CUDA kernel behind the C ABI against a plain PyTorch fp32 evaluation of the same
+op on the same (bf16-rounded) inputs.  Every check returns a dict of error statistics and raises AssertionError with
+a diagnostic message when out of tolerance.  Used by tests/test_kernels_gpu.py and tools/gpu_probe.py."""
+import math
+
+import torch
+
+from simple_tad_b200 import _lib as L
+
+DEV = "cuda"
+
+
+def _stats(got, ref, name, atol, rtol):
+    got = got.float()
+    ref = ref.float()
+    assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    finite = bool(torch.isfinite(got).all())
+    diff = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = diff > tol
+    nbad = int(bad.sum())
+    rel_l2 = float((got - ref).norm() / (ref.norm() + 1e-30))
+    out = {"name": name, "max_abs": float(diff.max()), "rel_l2": rel_l2, "n_bad": nbad, "n": got.numel(),
+           "finite": finite}
+    if nbad or not finite:
+        idx = bad.nonzero()[:8].tolist()
+        flat = bad.reshape(-1, bad.shape[-1]) if bad.dim() > 1 else bad.reshape(1, -1)
+        rows_bad = flat.any(1).nonzero().flatten()[:16].tolist()
+        cols_bad = flat.any(0).nonzero().flatten()[:16].tolist()
+        raise AssertionError(
+            f"{name}: {nbad}/{got.numel()} outside tol (atol={atol}, rtol={rtol}); finite={finite}; "
+            f"max_abs={out['max_abs']:.4g} rel_l2={rel_l2:.4g}; first bad idx={idx}; bad rows~{rows_bad}; "
+            f"bad cols~{cols_bad}; got={[float(got[tuple(i)]) for i in idx[:4]]} ref={[float(ref[tuple(i)]) for i in idx[:4]]}")
+    return out
+
+
+def _bf16(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(DEV)
+
+
+def _f32(*shape, scale=1.0, seed=0, shift=0.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale + shift).to(DEV)
+
+
+# ----------------------------------------------------------------------------------------------------- row kernels
+def check_cast(n=3 * 16 * 224 * 224 + 5):
+    x = _f32(n, seed=1)
+    y = L.cast_f32_bf16(x)
+    torch.cuda.synchronize()
+    assert torch.equal(y, x.to(torch.bfloat16)), "cast: not bit-identical to torch's round-to-nearest-even"
+    return {"name": "cast", "n": n}
+
+
+def check_row_stats(M=1000, D=768, eps=1e-6):
+    x = (_f32(M, D, seed=2, scale=1.5, shift=0.3)).to(torch.bfloat16)
+    st = L.row_stats(x, eps)
+    torch.cuda.synchronize()
+    xf = x.float()
+    mean = xf.mean(1)
+    rstd = (xf.var(1, unbiased=False) + eps).rsqrt()
+    a = _stats(st[:, 0], mean, f"row_stats.mean[{M}x{D}]", 1e-5, 1e-5)
+    b = _stats(st[:, 1], rstd, f"row_stats.rstd[{M}x{D}]", 1e-5, 1e-4)
+    return {"name": "row_stats", "mean": a, "rstd": b}
+
+
+def check_layernorm(M=777, D=768, eps=1e-6):
+    x = (_f32(M, D, seed=3, scale=2.0, shift=-0.2)).to(torch.bfloat16)
+    g = _f32(D, seed=4, scale=0.2, shift=1.0)
+    b = _f32(D, seed=5, scale=0.2)
+    y = L.layernorm(x, g, b, eps)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), g, b, eps)
+    return _stats(y, ref, f"layernorm[{M}x{D}]", 1e-4, 1e-4)
+
+
+def check_pool_head(B=5, N=1568, D=768, Cn=2, eps=1e-6):
+    x = (_f32(B, N, D, seed=6, scale=1.0, shift=0.1)).to(torch.bfloat16)
+    g = _f32(D, seed=7, scale=0.2, shift=1.0)
+    b = _f32(D, seed=8, scale=0.2)
+    w = _f32(Cn, D, seed=9, scale=0.05)
+    bh = _f32(Cn, seed=10, scale=0.1)
+    logits, probs = L.pool_norm_head(x, g, b, w, bh, eps, want_probs=True)
+    torch.cuda.synchronize()
+    pooled = x.float().mean(1)
+    ref = torch.nn.functional.layer_norm(pooled, (D,), g, b, eps) @ w.t() + bh
+    a = _stats(logits, ref, f"pool_head.logits[B{B},N{N},D{D}]", 2e-4, 2e-4)
+    p = _stats(probs, ref.softmax(-1), "pool_head.probs", 1e-4, 1e-4)
+    return {"name": "pool_head", "logits": a, "probs": p}
+
+
+# ----------------------------------------------------------------------------------------------------------- GEMMs
+def check_gemm(M=1568, N=768, K=768, mode="plain", seed=0):
+    """mode: plain | bias | resid | ln | ln_gelu"""
+    a = _bf16(M, K, seed=seed + 11, scale=1.0)
+    w = _bf16(N, K, seed=seed + 12, scale=0.05)
+    bias = _f32(N, seed=seed + 13, scale=0.5)
+    af, wf = a.float(), w.float()
+    if mode in ("plain", "bias", "resid"):
+        res = _bf16(M, N, seed=seed + 14) if mode == "resid" else None
+        out = L.gemm_bias_residual(a, w, None if mode == "plain" else bias, res)
+        torch.cuda.synchronize()
+        ref = af @ wf.t()
+        if mode != "plain":
+            ref = ref + bias
+        if mode == "resid":
+            ref = ref + res.float()
+    else:
+        eps = 1e-6
+        # x has a per-row offset so the folded mean term matters
+        a = (a.float() + _f32(M, 1, seed=seed + 15, scale=0.5)).to(torch.bfloat16)
+        af = a.float()
+        stats = L.row_stats(a, eps)
+        colsum = wf.sum(1).contiguous()
+        out = L.ln_gemm(a, stats, w, bias, colsum, gelu=(mode == "ln_gelu"))
+        torch.cuda.synchronize()
+        mean = af.mean(1, keepdim=True)
+        rstd = (af.var(1, unbiased=False, keepdim=True) + eps).rsqrt()
+        ref = ((af - mean) * rstd) @ wf.t() + bias
+        if mode == "ln_gelu":
+            ref = torch.nn.functional.gelu(ref)
+    # bf16 output rounding: 2^-8 relative; fp32 accumulation error is far smaller
+    return _stats(out, ref, f"gemm.{mode}[{M}x{N}x{K}]", 2e-2, 1e-2)
+
+
+# ------------------------------------------------------------------------------------------------------- attention
+def check_attention(B=2, H=3, S=1568, peaky=1.0, seed=0):
+    qkv = _bf16(B, S, 3, H, 64, seed=seed + 21, scale=1.0)
+    if peaky != 1.0:
+        qkv[:, :, 0] *= peaky  # sharper softmax -> exercises the running-max rescale
+    out = L.attention(qkv)
+    torch.cuda.synchronize()
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3).float() for i in range(3))  # [B,H,S,64]
+    att = (q * 64 ** -0.5) @ k.transpose(-1, -2)
+    ref = (att.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B, S, H * 64)
+    return _stats(out, ref, f"attention[B{B},H{H},S{S},peaky{peaky}]", 2e-2, 2e-2)
+
+
+# ----------------------------------------------------------------------------------------------------- patch embed
+def _sinusoid(n, d):
+    pos = torch.arange(n, dtype=torch.float64)[:, None]
+    j = torch.arange(d, dtype=torch.float64)[None, :]
+    ang = pos / torch.pow(torch.tensor(10000.0, dtype=torch.float64), 2 * torch.div(j, 2, rounding_mode="floor") / d)
+    tab = torch.where((torch.arange(d) % 2 == 0)[None, :], ang.sin(), ang.cos())
+    return tab.float()
+
+
+def check_patch_embed(B=2, D=384, mode="clips", masked=False, seed=0):
+    Cc, T, Hh, Ww = 3, 16, 224, 224
+    K = Cc * 2 * 16 * 16
+    N = 8 * 14 * 14
+    w5 = _bf16(D, Cc, 2, 16, 16, seed=seed + 31, scale=0.03)
+    bias = _f32(D, seed=seed + 32, scale=0.2)
+    pos_bias = (_sinusoid(N, D).to(DEV) + bias).contiguous()
+    dims = L.make_dims(dim=D, depth=1, heads=D // 64, hidden=4 * D)
+    if mode == "clips":
+        x = _bf16(B, Cc, T, Hh, Ww, seed=seed + 33)
+        clips = x
+        kw = dict(mode=L.STAD_IN_CLIPS)
+    else:
+        F, start, stride = 16 + 3 * (B - 1) + 2, 1, 3
+        frames = _bf16(F, Cc, Hh, Ww, seed=seed + 34)
+        x = frames
+        clips = torch.stack([frames[start + b * stride: start + b * stride + T] for b in range(B)])  # [B,T,C,H,W]
+        clips = clips.permute(0, 2, 1, 3, 4).contiguous()
+        kw = dict(mode=L.STAD_IN_FRAMES, n_frames=F, start=start, stride=stride)
+    ref = torch.nn.functional.conv3d(clips.float(), w5.float(), None, stride=(2, 16, 16))  # [B,D,8,14,14]
+    ref = ref.flatten(2).transpose(1, 2) + pos_bias  # [B,N,D]
+    tok_idx = None
+    n_tok = N
+    if masked:
+        g = torch.Generator().manual_seed(seed + 35)
+        keep = torch.stack([torch.randperm(196, generator=g)[:20].sort().values for _ in range(B)])  # [B,20]
+        tok = (torch.arange(8)[None, :, None] * 196 + keep[:, None, :]).reshape(B, -1)                # [B,160]
+        tok_idx = tok.to(torch.int32).to(DEV).contiguous()
+        n_tok = tok.shape[1]
+        ref = torch.gather(ref, 1, tok.to(DEV)[:, :, None].expand(-1, -1, D))
+    out = L.patch_embed(x, w5.reshape(D, K).contiguous(), pos_bias, dims, B, n_tok, tok_idx=tok_idx, **kw)
+    torch.cuda.synchronize()
+    return _stats(out.reshape(B, n_tok, D), ref, f"patch_embed[{mode},masked={masked},B{B},D{D}]", 2e-2, 1e-2)
+
+
+CHECKS = {
+    "cast": lambda: check_cast(),
+    "row_stats": lambda: [check_row_stats(1000, 768), check_row_stats(333, 384), check_row_stats(129, 1024)],
+    "layernorm": lambda: check_layernorm(),
+    "pool_head": lambda: [check_pool_head(5, 1568, 768), check_pool_head(3, 160, 384), check_pool_head(2, 1568, 1024)],
+    "gemm_plain_small": lambda: check_gemm(128, 64, 64, "plain"),
+    "gemm_plain_k": lambda: check_gemm(128, 128, 768, "plain"),
+    "gemm_plain": lambda: [check_gemm(1568, 768, 768, "plain"), check_gemm(6272, 2304, 768, "plain"),
+                           check_gemm(25088, 768, 3072, "plain")],
+    "gemm_bn": lambda: [check_gemm(4 * 1568, 384, 384, "bias"), check_gemm(40 * 1568, 1152, 384, "bias"),
+                        check_gemm(40 * 1568, 1024, 1024, "bias"), check_gemm(300, 1536, 384, "bias")],
+    "gemm_resid": lambda: [check_gemm(3136, 768, 768, "resid"), check_gemm(1568 * 3, 1024, 4096, "resid")],
+    "gemm_ln": lambda: [check_gemm(3136, 2304, 768, "ln"), check_gemm(1568, 1152, 384, "ln")],
+    "gemm_ln_gelu": lambda: [check_gemm(3136, 3072, 768, "ln_gelu"), check_gemm(1568, 4096, 1024, "ln_gelu")],
+    "attention_small": lambda: check_attention(1, 1, 128),
+    "attention_tail": lambda: [check_attention(1, 2, 160), check_attention(2, 1, 392)],
+    "attention": lambda: [check_attention(2, 3, 1568), check_attention(1, 12, 1568, peaky=6.0)],
+    "patch_embed": lambda: [check_patch_embed(2, 384, "clips"), check_patch_embed(3, 768, "clips")],
+    "patch_embed_frames": lambda: check_patch_embed(3, 384, "frames"),
+    "patch_embed_masked": lambda: [check_patch_embed(2, 768, "clips", masked=True),
+                                   check_patch_embed(2, 384, "frames", masked=True)],
+}

@@ -1,0 +1,14 @@
+"""GPU parity of every kernel behind the C ABI against PyTorch fp32 (see tests/kernel_checks.py)."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", [
+    "cast", "row_stats", "layernorm", "pool_head", "gemm_plain_small", "gemm_plain_k", "gemm_plain", "gemm_bn",
+    "gemm_resid", "gemm_ln", "gemm_ln_gelu", "attention_small", "attention_tail", "attention", "patch_embed",
+    "patch_embed_frames", "patch_embed_masked",
+])
+def test_kernel(name):
+    from tests.kernel_checks import CHECKS
+    CHECKS[name]()
