@@ -106,6 +106,14 @@ typedef struct stad_model {
   float attn_scale;    /* head_dim ** -0.5 (mf:67) */
 } stad_model;
 
+/* Where stad_vit_forward writes its results; any pointer may be NULL (nothing is written for it). */
+typedef struct stad_outputs {
+  float* logits;   /* [B, num_classes]  head output, mf:334                                   (classifier models) */
+  float* probs;    /* [B, num_classes]  softmax(logits), ris:381 / ri:107                     (classifier models) */
+  float* features; /* [B, D]            fc_norm(mean over tokens) = forward_features, mf:326  (classifier models) */
+  float* tokens;   /* [B, n_tok, D]     tokens after `norm`, mp:107-108                       (encoder models)    */
+} stad_outputs;
+
 /* ---- library ------------------------------------------------------------------------------------------------- */
 STAD_API int stad_abi_version(void);
 /* Binds nothing, checks that `device` is sm_100 and raises the kernels' shared-memory limits. Idempotent. */
@@ -124,10 +132,11 @@ STAD_API int stad_layernorm(const void* x, const float* g, const float* b, float
                    stad_stream_t stream);
 
 /* mean over tokens -> fc_norm -> head (-> softmax).   mf:325-326, mf:334, ris:381.
- * x[B, N, D] bf16; logits[B, C] fp32; probs[B, C] fp32 or NULL; scratch: >= B * 16 * D floats. */
+ * x[B, N, D] bf16; logits[B, C] fp32; probs[B, C] fp32 or NULL; features[B, D] fp32 (the fc_norm output that
+ * forward_features returns, mf:326) or NULL; scratch: >= B * 16 * D floats. */
 STAD_API int stad_pool_norm_head(const void* x, const float* g, const float* b, const float* w_head, const float* b_head,
-                        float* logits, float* probs, float* scratch, int B, int N, int D, int C, float eps,
-                        stad_stream_t stream);
+                        float* logits, float* probs, float* features, float* scratch, int B, int N, int D, int C,
+                        float eps, stad_stream_t stream);
 
 /* ---- tensor-core kernels (tcgen05 / TMEM / TMA) ---------------------------------------------------------------- */
 /* Tubelet patch embedding: Conv3d(k = s = (tubelet, patch, patch)) as an im2col-free GEMM + pos/bias table add.
@@ -158,12 +167,13 @@ STAD_API int stad_attention(const void* qkv, void* out, int B, int H, int S, flo
 STAD_API size_t stad_workspace_bytes(const stad_dims* dims, int B, int n_tok);
 
 /* VisionTransformer.forward (mf:308-335) / PretrainVisionTransformerEncoder.forward_features (mp:91-108).
- *   tok_idx NULL  -> classifier path: logits[B, C] (+ probs[B, C] if non-NULL).
- *   tok_idx given -> visible-token encoder path: tokens_out[B, n_tok, D] fp32 after `norm`; logits may be NULL.
+ *   tok_idx NULL  -> every token of every clip (n_tok must be the full token count).
+ *   tok_idx given -> int32[B, n_tok] visible-token ids: the masked-encoder path.
+ *   dims.num_classes > 0 -> classifier: out->logits required; out->probs / out->features optional.
+ *   dims.num_classes == 0 -> encoder: out->tokens required.
  * Returns the number of kernels launched (>= 0) or a negative error. */
 STAD_API int stad_vit_forward(const stad_model* model, const stad_input* in, const int32_t* tok_idx, int B, int n_tok,
-                     float* logits, float* probs, float* tokens_out, void* workspace, size_t workspace_bytes,
-                     stad_stream_t stream);
+                     const stad_outputs* out, void* workspace, size_t workspace_bytes, stad_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,203 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference) on the synthetic
+weights / inputs of oracle/synth.py.  Run in the build container (the reference is not present on the GPU box):
+
+    python -m oracle.make_golden            # all fixtures (~10 min of CPU)
+    python -m oracle.make_golden c1 peaky   # a subset
+
+Shims: `timm` is not installed, so the four symbols the reference imports from it are provided
+(timm.models.layers.{drop_path,to_2tuple,trunc_normal_}, timm.models.registry.register_model); `natsort` is stubbed
+for run_inference_simple.py.  Neither touches the forward math.  The script also reports the max abs difference between
+the reference outputs and oracle/vit_oracle.py on the same inputs.
+"""
+import os
+import sys
+import time
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("STAD_REFERENCE", "/root/reference")
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import synth, vit_oracle  # noqa: E402
+
+HID_TOK = [0, 1, 13, 195, 196, 783, 1000, 1567]   # sampled tokens of the 1568
+HID_CH = [0, 1, 2, 63, 64, 191, 255, 383]         # sampled channels (valid for D >= 384)
+
+
+def install_shims():
+    if "timm" not in sys.modules:
+        timm = types.ModuleType("timm")
+        models = types.ModuleType("timm.models")
+        layers = types.ModuleType("timm.models.layers")
+        registry = types.ModuleType("timm.models.registry")
+
+        def drop_path(x, drop_prob=0.0, training=False):
+            if drop_prob == 0.0 or not training:
+                return x
+            raise RuntimeError("drop_path shim is eval-only")
+
+        def to_2tuple(v):
+            return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+        def trunc_normal_(tensor, mean=0.0, std=1.0, a=-2.0, b=2.0):
+            return torch.nn.init.trunc_normal_(tensor, mean=mean, std=std, a=a, b=b)
+
+        _reg = {}
+
+        def register_model(fn):
+            _reg[fn.__name__] = fn
+            return fn
+
+        layers.drop_path, layers.to_2tuple, layers.trunc_normal_ = drop_path, to_2tuple, trunc_normal_
+        registry.register_model, registry._model_entrypoints = register_model, _reg
+        timm.models, models.layers, models.registry = models, layers, registry
+        sys.modules.update({"timm": timm, "timm.models": models, "timm.models.layers": layers,
+                            "timm.models.registry": registry})
+    if "natsort" not in sys.modules:
+        ns = types.ModuleType("natsort")
+        ns.natsorted = sorted
+        sys.modules["natsort"] = ns
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+
+
+def ref_classifier(arch, sd):
+    """The reference VisionTransformer (modeling_finetune.py) in fp32 with the naive attention path."""
+    import modeling_finetune as mf
+    from functools import partial
+    D, depth, heads = synth.ARCHS[arch]
+    if arch in mf.__dict__:
+        model = mf.__dict__[arch](num_classes=2, all_frames=16, tubelet_size=2, use_flash_attn=False, init_scale=1.0,
+                                  final_reduction="fc_norm")
+    else:  # reduced-depth variant: same ctor the factories call (mf:340-342), only `depth` differs
+        model = mf.VisionTransformer(patch_size=16, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
+                                     norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=2, all_frames=16,
+                                     tubelet_size=2, use_flash_attn=False, init_scale=1.0, final_reduction="fc_norm")
+    missing = model.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return model.eval()
+
+
+def ref_encoder(arch, sd):
+    import modeling_pretrain as mp
+    from functools import partial
+    D, depth, heads = synth.ARCHS[arch]
+    enc = mp.PretrainVisionTransformerEncoder(
+        img_size=224, patch_size=16, in_chans=3, num_classes=0, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4,
+        qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), init_values=0., tubelet_size=2,
+        use_flash_attn=False)   # same kwargs PretrainVisionTransformer passes down (mp:215-232)
+    enc.load_state_dict(sd, strict=True)
+    return enc.eval()
+
+
+@torch.no_grad()
+def ref_hidden(model, x):
+    """Residual stream after patch-embed+pos and after each block, via forward hooks on the reference modules."""
+    hs = []
+    hooks = [blk.register_forward_hook(lambda m, i, o: hs.append(o.detach())) for blk in model.blocks]
+    pre = model.blocks[0].register_forward_pre_hook(lambda m, i: hs.append(i[0].detach()))
+    logits = model(x)
+    for h in hooks + [pre]:
+        h.remove()
+    return logits, hs
+
+
+def sample_hidden(hs):
+    tok = torch.tensor(HID_TOK)
+    ch = torch.tensor(HID_CH)
+    samp = torch.stack([h[:, tok][:, :, ch] for h in hs])            # [L+1, B, 8, 8]
+    rms = torch.stack([h.pow(2).mean((1, 2)).sqrt() for h in hs])    # [L+1, B]
+    return samp.numpy(), rms.numpy()
+
+
+def save(name, **arrs):
+    os.makedirs(GOLD, exist_ok=True)
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print(f"  wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def gen_classifier(name, arch, B=None, video_T=None, n_videos=1, seed=0, peaky=1.0, use_ris=False, check_oracle=True):
+    D, depth, heads = synth.ARCHS[arch]
+    sd = synth.make_state_dict(arch, seed=seed, peaky=peaky)
+    if video_T is None:
+        x = synth.make_clips(B, seed=seed)
+    else:
+        x = torch.cat([synth.windows_from_video(synth.make_video(video_T, seed=seed + v)) for v in range(n_videos)])
+    model = ref_classifier(arch, sd)
+    t0 = time.time()
+    logits, hs = [], None
+    for i in range(0, x.shape[0], 4):
+        if i == 0:
+            lg, hs = ref_hidden(model, x[:4])
+        else:
+            with torch.no_grad():
+                lg = model(x[i:i + 4])
+        logits.append(lg)
+    logits = torch.cat(logits)
+    print(f"{name}: reference {arch} on {tuple(x.shape)} in {time.time() - t0:.1f}s; logits[0]={logits[0].tolist()}")
+    samp, rms = sample_hidden(hs)
+    extra = {}
+    if use_ris:
+        import run_inference_simple as ris
+        m2 = ris.get_video_vit_small(with_flash=False) if D == 384 else ris.get_video_vit_base(with_flash=False)
+        m2.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            probs = m2.eval()(x)
+        assert torch.allclose(probs, logits.softmax(-1), atol=1e-6), "run_inference_simple model disagrees with modeling_finetune"
+        extra["probs_ris"] = probs.numpy()
+    if check_oracle:
+        o = vit_oracle.vit_forward(sd, x[:4], heads)
+        print(f"  oracle vs reference: max|dlogit| = {(o - logits[:4]).abs().max():.3e}")
+    save(name, logits=logits.numpy(), probs=logits.softmax(-1).numpy(), hidden_samples=samp, hidden_rms=rms,
+         hid_tok=np.array(HID_TOK), hid_ch=np.array(HID_CH), meta=np.array([seed, x.shape[0], peaky]), **extra)
+
+
+def gen_encoder(name, arch, B, ratio=0.9, seed=0):
+    D, depth, heads = synth.ARCHS[arch]
+    sd = synth.make_state_dict(arch, seed=seed, encoder=True)
+    x = synth.make_clips(B, seed=seed)
+    mask = synth.tube_mask(B, ratio, seed=seed)
+    enc = ref_encoder(arch, sd)
+    t0 = time.time()
+    with torch.no_grad():
+        y = enc(x, mask)
+    print(f"{name}: reference encoder {arch} {tuple(x.shape)} mask {ratio} -> {tuple(y.shape)} in {time.time() - t0:.1f}s")
+    o = vit_oracle.encoder_forward(sd, x, mask, heads)
+    print(f"  oracle vs reference: max|d| = {(o - y).abs().max():.3e}")
+    save(name, tokens=y.numpy().astype(np.float16), token_norm=y.norm(dim=-1).numpy(),
+         mask=mask.numpy(), meta=np.array([seed, B, ratio]))
+
+
+def main():
+    install_shims()
+    torch.set_num_threads(os.cpu_count())
+    want = set(sys.argv[1:])
+
+    def on(k):
+        return not want or k in want
+    # fast fixtures (also exercised by the CPU test-suite)
+    if on("small"):
+        gen_classifier("small_vits_d2_b2", "vit_small_d2", B=2, seed=11)
+        gen_encoder("small_enc_vitb_d2_b2", "vit_base_d2", B=2, seed=12)
+    if on("peaky"):
+        gen_classifier("peaky_vits_d2_b2", "vit_small_d2", B=2, seed=13, peaky=3.0)
+    # the five BASELINE.json configs
+    if on("c1"):
+        gen_classifier("c1_vits_b4", "vit_small_patch16_224", B=4, seed=1, use_ris=True)
+    if on("c2"):
+        gen_classifier("c2_vitb_video100", "vit_base_patch16_224", video_T=100, seed=2)
+    if on("c3"):
+        gen_classifier("c3_vitl_2x20", "vit_large_patch16_224", video_T=20, n_videos=2, seed=3)
+    if on("c4"):
+        gen_encoder("c4_enc_vitb_b4", "vit_base_patch16_224", B=4, seed=4)
+    if on("c5"):
+        gen_classifier("c5_vitb_b8", "vit_base_patch16_224", B=8, seed=5)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,10 @@ class StadModel(C.Structure):
                 ("eps", C.c_float), ("attn_scale", C.c_float)]
 
 
+class StadOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("logits", "probs", "features", "tokens")]
+
+
 _lib = None
 _inited_devices = set()
 
@@ -63,14 +67,14 @@ def load():
         "stad_cast_f32_bf16": (C.c_int, [vp, vp, sz, vp]),
         "stad_row_stats": (C.c_int, [vp, vp, i32, i32, f32, vp]),
         "stad_layernorm": (C.c_int, [vp, vp, vp, vp, i32, i32, f32, vp]),
-        "stad_pool_norm_head": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]),
+        "stad_pool_norm_head": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]),
         "stad_patch_embed": (C.c_int, [C.POINTER(StadInput), vp, vp, vp, vp, vp, C.POINTER(StadDims), i32, i32, vp]),
         "stad_ln_gemm": (C.c_int, [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp]),
         "stad_gemm_bias_residual": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "stad_attention": (C.c_int, [vp, vp, i32, i32, i32, f32, vp]),
         "stad_workspace_bytes": (sz, [C.POINTER(StadDims), i32, i32]),
-        "stad_vit_forward": (C.c_int, [C.POINTER(StadModel), C.POINTER(StadInput), vp, i32, i32, vp, vp, vp, vp, sz,
-                                       vp]),
+        "stad_vit_forward": (C.c_int, [C.POINTER(StadModel), C.POINTER(StadInput), vp, i32, i32,
+                                       C.POINTER(StadOutputs), vp, sz, vp]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -151,18 +155,20 @@ def layernorm(x, g, b, eps):
     return y
 
 
-def pool_norm_head(x, g, b, w_head, b_head, eps, want_probs=False):
+def pool_norm_head(x, g, b, w_head, b_head, eps, want_probs=False, want_features=False):
     init(x.device)
     _req(x, torch.bfloat16, "x")
     B, N, D = x.shape
     Cn = w_head.shape[0]
     logits = torch.empty(B, Cn, dtype=torch.float32, device=x.device)
     probs = torch.empty(B, Cn, dtype=torch.float32, device=x.device) if want_probs else None
+    feats = torch.empty(B, D, dtype=torch.float32, device=x.device) if want_features else None
     scratch = torch.empty(B * 16 * D, dtype=torch.float32, device=x.device)
     check(load().stad_pool_norm_head(ptr(x), ptr(g), ptr(b), ptr(_req(w_head, torch.float32, "w_head")), ptr(b_head),
-                                     ptr(logits), ptr(probs), ptr(scratch), B, N, D, Cn, eps, stream_ptr()),
-          "stad_pool_norm_head")
-    return (logits, probs) if want_probs else logits
+                                     ptr(logits), ptr(probs), ptr(feats), ptr(scratch), B, N, D, Cn, eps,
+                                     stream_ptr()), "stad_pool_norm_head")
+    res = (logits,) + ((probs,) if want_probs else ()) + ((feats,) if want_features else ())
+    return res if len(res) > 1 else logits
 
 
 def ln_gemm(x, stats, w, bias, colsum, gelu=False, out=None):

@@ -186,10 +186,10 @@ int stad_layernorm(const void* x, const float* g, const float* b, float* y, int 
 }
 
 int stad_pool_norm_head(const void* x, const float* g, const float* b, const float* w_head, const float* b_head,
-                        float* logits, float* probs, float* scratch, int B, int N, int D, int C, float eps,
-                        stad_stream_t stream) {
-  return launch_pool_norm_head(static_cast<const bf16*>(x), g, b, w_head, b_head, logits, probs, scratch, B, N, D, C,
-                               eps, as_stream(stream));
+                        float* logits, float* probs, float* features, float* scratch, int B, int N, int D, int C,
+                        float eps, stad_stream_t stream) {
+  return launch_pool_norm_head(static_cast<const bf16*>(x), g, b, w_head, b_head, logits, probs, features, scratch, B,
+                               N, D, C, eps, as_stream(stream));
 }
 
 int stad_patch_embed(const stad_input* in, const void* w, const float* pos_bias, const int32_t* tok_idx, void* out,
@@ -239,8 +239,13 @@ size_t stad_workspace_bytes(const stad_dims* dims, int B, int n_tok) {
   return carve(dims, B, n_tok, nullptr).bytes;
 }
 
-int stad_vit_forward(const stad_model* m, const stad_input* in, const int32_t* tok_idx, int B, int n_tok, float* logits,
-                     float* probs, float* tokens_out, void* workspace, size_t workspace_bytes, stad_stream_t stream_) {
+int stad_vit_forward(const stad_model* m, const stad_input* in, const int32_t* tok_idx, int B, int n_tok,
+                     const stad_outputs* out, void* workspace, size_t workspace_bytes, stad_stream_t stream_) {
+  STAD_CHECK_ARG(out != nullptr, "vit_forward: outputs is NULL");
+  float* logits = out->logits;
+  float* probs = out->probs;
+  float* features = out->features;
+  float* tokens_out = out->tokens;
   STAD_CHECK_ARG(m != nullptr && m->blocks != nullptr, "vit_forward: model is NULL");
   STAD_CHECK_ARG(B > 0 && n_tok > 0, "vit_forward: B=%d n_tok=%d", B, n_tok);
   const stad_dims* d = &m->dims;
@@ -294,8 +299,8 @@ int stad_vit_forward(const stad_model* m, const stad_input* in, const int32_t* t
 
   if (classifier) {
     // norm = Identity; mean over tokens; fc_norm; head                (mf:323-326, mf:334)
-    if ((rc = launch_pool_norm_head(ws.x, m->norm_g, m->norm_b, m->w_head, m->b_head, logits, probs, ws.pool, B, n_tok,
-                                    D, d->num_classes, m->eps, stream)))
+    if ((rc = launch_pool_norm_head(ws.x, m->norm_g, m->norm_b, m->w_head, m->b_head, logits, probs, features, ws.pool,
+                                    B, n_tok, D, d->num_classes, m->eps, stream)))
       return rc;
     launches += 2;
   } else {

@@ -38,9 +38,11 @@ const char* last_error();
 
 int sm_count();  // SMs of the current device (cached)
 
-// rank-N bf16 tensor map with 128-byte swizzle. dims/strides innermost-first; strides in BYTES for dims 1..rank-1.
+// rank-N bf16 tensor map. dims/strides innermost-first; strides in BYTES for dims 1..rank-1.
+// swizzle_bytes: 128 (default) or 32.  NOTE: TMA pads a box whose inner extent is narrower than the swizzle span up
+// to the span, so the inner box extent must equal the span for a dense shared-memory tile.
 int make_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box);
+                   const uint32_t* box, int swizzle_bytes = 128);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

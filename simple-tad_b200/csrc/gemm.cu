@@ -7,7 +7,9 @@
 //
 // Replaces every nn.Linear / F.linear on the reference path (modeling_finetune.py:48,52,92,104,119,128) and, in
 // patch mode, the Conv3d of PatchEmbed (modeling_finetune.py:181-190): the A operand is then fetched with a 5-D tensor
-// map straight out of the [.., H, W] clip planes (im2col-free), k order (c, dt, dh, dw) = Conv3d weight order.
+// map straight out of the [.., H, W] clip planes (im2col-free), k order (c, dt, dh, dw) = Conv3d weight order.  One
+// TMA box = the 16 dw pixels of one (c, dt, dh) line for every token of the tile = one UMMA K-slice, stored as
+// 32-byte rows (SWIZZLE_32B, so the box is dense); four such boxes make one 64-wide k chunk.
 //
 // Roofline: dense BF16 tensor. Algorithmic FLOPs = 2 M N K; HBM bytes = 2 (M K + N K + M N) (+ 2 M N residual).
 #include "kernels.h"
@@ -132,7 +134,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           pe_tp = (m_tile / g.h_tiles) % g.Tp;
           pe_b = m_tile / (g.h_tiles * g.Tp);
           pe_h0 = hh * g.hp_tile;
-          a_bytes = g.Wp * g.hp_tile * BK * 2;  // full box, out-of-range h' rows arrive as zeros
+          a_bytes = g.Wp * g.hp_tile * BK * 2;  // 4 full boxes, out-of-range h' rows arrive as zeros
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -148,7 +150,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int t = pe_tp * g.tubelet + dt;
             const int plane = g.mode == STAD_IN_CLIPS ? (pe_b * g.C + c) * g.T + t
                                                       : (g.start + pe_b * g.stride + t) * g.C + c;
-            tma_load_5d(sa, &tmap_a, &full_bar[stage], 0, dh0, 0, pe_h0, plane);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)  // K-slice k = line dh0 + k: [tokens][16 dw] at sa + k * 4 KB
+              tma_load_5d(sa + k * (BM * UMMA_K * 2), &tmap_a, &full_bar[stage], 0, 0, pe_h0, dh0 + k, plane);
           } else {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_tile * BM);
           }
@@ -178,12 +182,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
-          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+          if constexpr (kPatch) {
+            // A: four K-slices of [128 tokens][32 B] rows (SWIZZLE_32B, 8-row groups 256 B apart), 4 KB each
+            const uint64_t da = make_smem_desc(sa, 16, 256, kLayoutSw32);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_ss(tmem_d, da + k * (BM * UMMA_K * 2 >> 4), db + 2 * k, idesc, (kb | k) != 0);
+          } else {
+            const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+              umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
           }
           umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
           if (++stage == C::STAGES) {
@@ -413,12 +425,12 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     const PatchGeom& pg = *g.patch;
     ka.pg = pg;
     ka.m_tiles = (g.M / (pg.Tp * pg.Hp * pg.Wp)) * pg.Tp * pg.h_tiles;
-    // dims innermost-first: dw(16) dh(16) w'(Wp) h'(Hp) plane
-    const uint64_t dims[5] = {16, 16, (uint64_t)pg.Wp, (uint64_t)pg.Hp, (uint64_t)pg.n_planes};
-    const uint64_t strides[4] = {(uint64_t)pg.img_w * 2, 32, (uint64_t)pg.img_w * 32,
+    // dims innermost-first: dw(16) w'(Wp) h'(Hp) dh(16) plane; box = one (dh, plane) line of every token of the tile
+    const uint64_t dims[5] = {16, (uint64_t)pg.Wp, (uint64_t)pg.Hp, 16, (uint64_t)pg.n_planes};
+    const uint64_t strides[4] = {32, (uint64_t)pg.img_w * 32, (uint64_t)pg.img_w * 2,
                                  (uint64_t)pg.img_h * pg.img_w * 2};
-    const uint32_t box[5] = {16, 4, (uint32_t)pg.Wp, (uint32_t)pg.hp_tile, 1};
-    if ((rc = make_tmap_bf16(&ta, g.a, 5, dims, strides, box))) return rc;
+    const uint32_t box[5] = {16, (uint32_t)pg.Wp, (uint32_t)pg.hp_tile, 1, 1};
+    if ((rc = make_tmap_bf16(&ta, g.a, 5, dims, strides, box, 32))) return rc;
   } else {
     ka.m_tiles = ceil_div(g.M, BM);
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.M};

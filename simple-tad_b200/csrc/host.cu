@@ -45,7 +45,7 @@ int sm_count() {
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+                   const uint32_t* box, int swizzle_bytes) {
   std::call_once(g_encode_once, load_encode);
   if (!g_encode) return fail(STAD_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if (reinterpret_cast<uintptr_t>(gptr) & 15) return fail(STAD_E_ALIGN, "tensor map base must be 16-byte aligned");
@@ -63,8 +63,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t*
                                         (unsigned long long)gstr[i - 1]);
     }
   }
+  if (swizzle_bytes != 128 && swizzle_bytes != 32) return fail(STAD_E_SHAPE, "tensor map: swizzle %d unsupported", swizzle_bytes);
+  if (box[0] * 2 != (uint32_t)swizzle_bytes)
+    return fail(STAD_E_SHAPE, "tensor map: inner box (%u B) must equal the swizzle span (%d B)", box[0] * 2, swizzle_bytes);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(gptr), gdim, gstr,
-                        bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(STAD_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu,%llu box %u,%u)", (int)r,

@@ -44,8 +44,8 @@ int launch_row_stats(const bf16* x, float2* stats, int M, int D, float eps, cuda
 int launch_layernorm(const bf16* x, const float* g, const float* b, float* y, int M, int D, float eps,
                      cudaStream_t stream);
 int launch_pool_norm_head(const bf16* x, const float* g, const float* b, const float* w_head, const float* b_head,
-                          float* logits, float* probs, float* scratch, int B, int N, int D, int C, float eps,
-                          cudaStream_t stream);
+                          float* logits, float* probs, float* features, float* scratch, int B, int N, int D, int C,
+                          float eps, cudaStream_t stream);
 // visible-token im2col: out[B*n_tok, K] bf16 rows (c, dt, dh, dw) of the listed tokens
 int launch_gather_patches(const bf16* planes, const PatchGeom& pg, const int32_t* tok_idx, bf16* out, int B,
                           int n_tok, cudaStream_t stream);

@@ -212,14 +212,19 @@ STAD_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" 
 // K-major tile  (rows of 64 bf16 = 128 B, 8-row groups 1024 B apart): SBO = 1024, LBO unused.
 // MN-major tile (64 MN elements = one 128 B row per k, 8 k-rows per 1024 B group): SBO = 1024 between k-groups,
 //               LBO = distance between 64-wide MN atoms (unused when MN extent is 64).
-STAD_DEVICE uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+STAD_DEVICE uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout) << 61;
   return d;
+}
+constexpr uint32_t kLayoutSw128 = 2;  // 128-byte rows, 8-row groups of 1024 B
+constexpr uint32_t kLayoutSw32 = 6;   //  32-byte rows, 8-row groups of  256 B
+STAD_DEVICE uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_smem_desc(smem_addr, lbo_bytes, sbo_bytes, kLayoutSw128);
 }
 
 // Instruction descriptor for kind::f16 with BF16 inputs and FP32 accumulation.

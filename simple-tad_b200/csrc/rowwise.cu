@@ -164,7 +164,7 @@ STAD_DEVICE float block_sum(float v, float* sh) {
 __global__ void __launch_bounds__(256)
 pool_head_kernel(const float* __restrict__ partial, const float* __restrict__ g, const float* __restrict__ b,
                  const float* __restrict__ w_head, const float* __restrict__ b_head, float* __restrict__ logits,
-                 float* __restrict__ probs, int N, int D, int C, float eps) {
+                 float* __restrict__ probs, float* __restrict__ features, int N, int D, int C, float eps) {
   extern __shared__ float sm[];  // [D] pooled / normalised vector, then [32] scratch, then [C] logits
   float* vec = sm;
   float* sh = sm + D;
@@ -187,7 +187,11 @@ pool_head_kernel(const float* __restrict__ partial, const float* __restrict__ g,
   }
   const float var = block_sum(q, sh) / static_cast<float>(D);
   const float rstd = rsqrtf(var + eps);
-  for (int c = threadIdx.x; c < D; c += blockDim.x) vec[c] = fmaf((vec[c] - mean) * rstd, g[c], b[c]);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float y = fmaf((vec[c] - mean) * rstd, g[c], b[c]);
+    vec[c] = y;
+    if (features != nullptr) features[static_cast<size_t>(bidx) * D + c] = y;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int cls = warp; cls < C; cls += nw) {
@@ -287,8 +291,8 @@ int launch_layernorm(const bf16* x, const float* g, const float* b, float* y, in
 }
 
 int launch_pool_norm_head(const bf16* x, const float* g, const float* b, const float* w_head, const float* b_head,
-                          float* logits, float* probs, float* scratch, int B, int N, int D, int C, float eps,
-                          cudaStream_t stream) {
+                          float* logits, float* probs, float* features, float* scratch, int B, int N, int D, int C,
+                          float eps, cudaStream_t stream) {
   STAD_CHECK_ARG(B > 0 && N > 0 && C > 0 && C <= 1024, "pool_norm_head: bad sizes B=%d N=%d C=%d", B, N, C);
   STAD_CHECK_ARG(D % 8 == 0 && D >= 8 && D <= 2048, "pool_norm_head: D=%d must be a multiple of 8 and <= 2048", D);
   if (reinterpret_cast<uintptr_t>(x) & 15) return fail(STAD_E_ALIGN, "pool_norm_head: x must be 16-byte aligned");
@@ -299,7 +303,7 @@ int launch_pool_norm_head(const bf16* x, const float* g, const float* b, const f
   pool_partial_kernel<<<dim3(kPoolChunks, B), threads, smem1, stream>>>(x, scratch, N, D);
   STAD_LAUNCH_OK("pool_partial");
   const size_t smem2 = (static_cast<size_t>(D) + 32 + C) * sizeof(float);
-  pool_head_kernel<<<B, threads, smem2, stream>>>(scratch, g, b, w_head, b_head, logits, probs, N, D, C, eps);
+  pool_head_kernel<<<B, threads, smem2, stream>>>(scratch, g, b, w_head, b_head, logits, probs, features, N, D, C, eps);
   STAD_LAUNCH_OK("pool_head");
   return STAD_OK;
 }

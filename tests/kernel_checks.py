@@ -81,13 +81,15 @@ def check_pool_head(B=5, N=1568, D=768, Cn=2, eps=1e-6):
     b = _f32(D, seed=8, scale=0.2)
     w = _f32(Cn, D, seed=9, scale=0.05)
     bh = _f32(Cn, seed=10, scale=0.1)
-    logits, probs = L.pool_norm_head(x, g, b, w, bh, eps, want_probs=True)
+    logits, probs, feats = L.pool_norm_head(x, g, b, w, bh, eps, want_probs=True, want_features=True)
     torch.cuda.synchronize()
     pooled = x.float().mean(1)
-    ref = torch.nn.functional.layer_norm(pooled, (D,), g, b, eps) @ w.t() + bh
+    normed = torch.nn.functional.layer_norm(pooled, (D,), g, b, eps)
+    ref = normed @ w.t() + bh
     a = _stats(logits, ref, f"pool_head.logits[B{B},N{N},D{D}]", 2e-4, 2e-4)
     p = _stats(probs, ref.softmax(-1), "pool_head.probs", 1e-4, 1e-4)
-    return {"name": "pool_head", "logits": a, "probs": p}
+    f = _stats(feats, normed, "pool_head.features", 1e-4, 1e-4)
+    return {"name": "pool_head", "logits": a, "probs": p, "features": f}
 
 
 # ----------------------------------------------------------------------------------------------------------- GEMMs
