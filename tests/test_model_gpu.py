@@ -18,7 +18,7 @@ def _hidden_states_gpu(model, x):
     from simple_tad_b200 import _lib
     prep = model.prepare(x.device)
     B = x.shape[0]
-    h = model.patch_embed(x) + (model.pos_embed.to(x.device) if True else 0)
+    h = model.patch_embed(x) + model.pos_embed.to(x.device)
     hs = [h]
     for blk in model.blocks:
         h = blk(h)
