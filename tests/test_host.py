@@ -1,0 +1,113 @@
+"""CPU: host-side logic of the drop-in modules — registry, checkpoint naming contract, weight preparation
+(LayerNorm folding), position table, token index lists.  No kernel is launched."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import synth, vit_oracle
+from simple_tad_b200 import modeling_finetune as mf
+from simple_tad_b200 import modeling_pretrain as mp
+from simple_tad_b200.registry import create_model, is_model, list_models
+
+
+def test_registry_has_every_reference_factory():
+    for name in ("vit_small_patch16_224", "vit_base_patch16_224", "vit_base_patch16_384", "vit_large_patch16_224",
+                 "vit_large_patch16_384", "vit_large_patch16_512", "vit_huge_patch16_224",
+                 "pretrain_videomae_small_patch16_224", "pretrain_videomae_base_patch16_224",
+                 "pretrain_videomae_large_patch16_224", "pretrain_videomae_huge_patch16_224"):
+        assert is_model(name), name
+    assert len(list_models()) >= 11
+    with pytest.raises(RuntimeError):
+        create_model("vit_tiny_does_not_exist")
+
+
+def test_create_model_call_site_of_run_frame_finetuning():
+    """rff:374-389 passes drop_block_rate=None, which the ctor does not accept: create_model must drop None kwargs."""
+    m = create_model("vit_small_patch16_224", pretrained=False, num_classes=2, all_frames=16, tubelet_size=2,
+                     fc_drop_rate=0.0, drop_rate=0.0, drop_path_rate=0.1, attn_drop_rate=0.0, drop_block_rate=None,
+                     use_checkpoint=False, final_reduction="fc_norm", init_scale=0.001, use_flash_attn=True)
+    assert sum(p.numel() for p in m.parameters()) == 21_880_706   # ViT-S 21.88 M params
+    assert m.get_num_layers() == 12 and m.num_heads == 6
+    assert m.patch_embed.patch_size == (16, 16) and m.patch_embed.num_patches == 1568 and m.patch_embed.tubelet_size == 2
+    assert m.pos_embed.shape == (1, 1568, 384) and "pos_embed" not in m.state_dict()
+    assert m.no_weight_decay() == {"pos_embed", "cls_token"}
+    assert m.default_cfg["num_classes"] == 400
+    assert float(m.head.weight.abs().max()) < 1e-3  # init_scale applied (mf:281-283)
+    assert isinstance(m.blocks[3].drop_path, mf.DropPath) and isinstance(m.blocks[0].drop_path, torch.nn.Identity)
+
+
+def test_state_dict_contract_matches_reference_names_and_shapes():
+    for arch, factory in (("vit_small_patch16_224", mf.vit_small_patch16_224), ("vit_base_patch16_224", mf.vit_base_patch16_224)):
+        sd = synth.make_state_dict(arch)
+        m = factory(num_classes=2)
+        own = m.state_dict()
+        assert set(own) == set(sd)
+        for k in sd:
+            assert own[k].shape == sd[k].shape, k
+        assert "blocks.0.attn.qkv.bias" not in own and "blocks.0.attn.q_bias" in own  # K has no bias (mf:69-75)
+    enc = mp.pretrain_videomae_base_patch16_224(decoder_depth=4)
+    sde = synth.make_state_dict("vit_base_patch16_224", encoder=True)
+    assert set(enc.state_dict()) == set(sde) and "norm.weight" in sde and "head.weight" not in sde
+
+
+def test_sinusoid_table_is_bit_identical_to_the_oracle():
+    a = mf.get_sinusoid_encoding_table(1568, 384)
+    b = vit_oracle.sinusoid_table(1568, 384)
+    assert a.dtype == torch.float32 and a.shape == (1, 1568, 384)
+    assert torch.equal(a, b)
+
+
+def test_layernorm_fold_is_algebraically_exact():
+    """LN(x) W^T + b == rstd * (x W'^T - mean * colsum(W')) + b'   with W' = W diag(gamma), b' = b + W beta."""
+    torch.manual_seed(0)
+    D = 384
+    blk = mf.Block(D, 6, qkv_bias=True, init_values=0., norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6)).eval()
+    with torch.no_grad():
+        for p in blk.parameters():
+            p.copy_(torch.randn_like(p) * 0.05 + (1.0 if p.dim() == 1 and p is blk.norm1.weight else 0.0))
+    pk = blk.packed("cpu")
+    x = torch.randn(50, D) * 2 + 0.5
+    mean = x.mean(1, keepdim=True)
+    rstd = (x.var(1, unbiased=False, keepdim=True) + 1e-6).rsqrt()
+    ref = F.linear(F.layer_norm(x, (D,), blk.norm1.weight, blk.norm1.bias, 1e-6), blk.attn.qkv.weight, blk.attn.packed_qkv_bias())
+    w = pk["w_qkv"].float()
+    got = rstd * (x @ w.t() - mean * pk["cs_qkv"]) + pk["b_qkv"]
+    # only the bf16 rounding of W' separates the two
+    assert float((got - ref).abs().max()) < 2e-2 * float(ref.abs().max())
+    assert torch.equal(pk["cs_qkv"], w.sum(1))
+    D3 = 3 * D
+    assert pk["w_qkv"].shape == (D3, D) and pk["w_fc1"].shape == (4 * D, D) and pk["w_fc2"].shape == (D, 4 * D)
+    # K rows get no bias except the beta term
+    k_bias = pk["b_qkv"][D:2 * D]
+    assert torch.allclose(k_bias, blk.attn.qkv.weight[D:2 * D] @ blk.norm1.bias, atol=1e-5)
+
+
+def test_layer_scale_is_folded_into_proj_and_fc2():
+    blk = mf.Block(384, 6, qkv_bias=True, init_values=0.1, norm_layer=lambda d: torch.nn.LayerNorm(d, eps=1e-6)).eval()
+    pk = blk.packed("cpu")
+    assert torch.allclose(pk["w_proj"].float(), (blk.attn.proj.weight * 0.1).to(torch.bfloat16).float())
+    assert torch.allclose(pk["b_fc2"], blk.mlp.fc2.bias * 0.1)
+
+
+def test_visible_token_indices_match_boolean_indexing_order():
+    mask = synth.tube_mask(5, 0.9, seed=3)
+    idx, n = mp.visible_token_indices(mask)
+    assert n == 160 and idx.dtype == torch.int32
+    assert torch.equal(idx, vit_oracle.visible_indices(mask))
+    idx75, n75 = mp.visible_token_indices(synth.tube_mask(2, 0.75, seed=1))
+    assert n75 == 392
+
+
+def test_inference_only_and_cuda_only():
+    m = mf.vit_small_patch16_224(num_classes=2)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        m.train()(torch.zeros(1, 3, 16, 224, 224))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.eval()(torch.zeros(1, 3, 16, 224, 224))
+    with pytest.raises(NotImplementedError):
+        mf.VisionTransformer(embed_dim=384, depth=1, num_heads=6, num_classes=2, final_reduction="cls").eval().prepare("cpu")
+    with pytest.raises(NotImplementedError, match="head_dim"):
+        mf.vit_huge_patch16_224(num_classes=2).eval().prepare("cpu")

@@ -1,0 +1,111 @@
+"""CPU: the oracle restatement (oracle/vit_oracle.py) against the golden outputs of the UNMODIFIED reference
+(tests/golden/*.npz, written by oracle/make_golden.py from /root/reference).  This is what pins parity."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth, vit_oracle
+from tests import parity
+
+ATOL = 2e-5  # fp32 CPU arithmetic on both sides; only thread-count / blocking differences remain
+
+
+def _check_hidden(g, hidden):
+    tok = torch.as_tensor(g["hid_tok"])
+    ch = torch.as_tensor(g["hid_ch"])
+    samp = torch.stack([h[:, tok][:, :, ch] for h in hidden]).numpy()
+    n = samp.shape[1]
+    np.testing.assert_allclose(samp, g["hidden_samples"][:, :n], atol=5e-4, rtol=1e-4)
+    rms = torch.stack([h.pow(2).mean((1, 2)).sqrt() for h in hidden]).numpy()
+    np.testing.assert_allclose(rms, g["hidden_rms"][:, :n], rtol=1e-4)
+
+
+@pytest.mark.parametrize("fixture,arch,seed,peaky", [
+    ("small_vits_d2_b2", "vit_small_d2", 11, 1.0),
+    ("peaky_vits_d2_b2", "vit_small_d2", 13, 3.0),
+])
+def test_small_classifier_logits_and_hidden(fixture, arch, seed, peaky):
+    g = parity.golden(fixture)
+    D, depth, heads = synth.ARCHS[arch]
+    sd = synth.make_state_dict(arch, seed=seed, peaky=peaky)
+    x = synth.make_clips(2, seed=seed)
+    logits, hidden = vit_oracle.vit_forward(sd, x, heads, return_hidden=True)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], atol=ATOL)
+    np.testing.assert_allclose(logits.softmax(-1).numpy(), g["probs"], atol=ATOL)
+    _check_hidden(g, hidden)
+    # the fixture is informative: probabilities are neither 0.5 nor saturated (SURVEY §8c pitfall)
+    p = g["probs"][:, 1]
+    assert (np.abs(p - 0.5) > 0.02).all() and (p > 1e-3).all() and (p < 1 - 1e-3).all()
+
+
+def test_small_encoder_tokens():
+    g = parity.golden("small_enc_vitb_d2_b2")
+    D, depth, heads = synth.ARCHS["vit_base_d2"]
+    sd = synth.make_state_dict("vit_base_d2", seed=12, encoder=True)
+    x = synth.make_clips(2, seed=12)
+    mask = synth.tube_mask(2, 0.9, seed=12)
+    assert (mask.numpy() == g["mask"]).all()
+    y = vit_oracle.encoder_forward(sd, x, mask, heads)
+    assert y.shape == (2, 160, D)
+    np.testing.assert_allclose(y.norm(dim=-1).numpy(), g["token_norm"], rtol=1e-4)
+    np.testing.assert_allclose(y.numpy(), g["tokens"].astype(np.float32), atol=2e-2, rtol=2e-3)  # fp16 storage
+
+
+def test_config1_vits_two_clips_match_run_inference_simple():
+    """Config 1 (first two of the four clips, to bound CPU time): probabilities of the reference's
+    run_inference_simple.VisionTransformerInfer (softmax inside forward, ris:378-382)."""
+    g = parity.golden("c1_vits_b4")
+    sd = synth.make_state_dict("vit_small_patch16_224", seed=1)
+    x = synth.make_clips(4, seed=1)[:2]
+    probs = vit_oracle.vit_probs(sd, x, 6)
+    np.testing.assert_allclose(probs.numpy(), g["probs_ris"][:2], atol=ATOL)
+    np.testing.assert_allclose(probs.numpy(), g["probs"][:2], atol=ATOL)
+
+
+def test_config2_vitb_one_window_of_the_video():
+    g = parity.golden("c2_vitb_video100")
+    assert g["logits"].shape == (85, 2)  # 100 frames -> 85 stride-1 windows (dota.py:209-223)
+    sd = synth.make_state_dict("vit_base_patch16_224", seed=2)
+    frames = synth.make_video(100, seed=2)
+    clip = synth.windows_from_video(frames, start=40, count=1)
+    logits = vit_oracle.vit_forward(sd, clip, 12)
+    np.testing.assert_allclose(logits.numpy(), g["logits"][40:41], atol=ATOL)
+
+
+def test_config4_encoder_one_clip():
+    g = parity.golden("c4_enc_vitb_b4")
+    sd = synth.make_state_dict("vit_base_patch16_224", seed=4, encoder=True)
+    x = synth.make_clips(4, seed=4)[:1]
+    mask = synth.tube_mask(4, 0.9, seed=4)[:1]
+    y = vit_oracle.encoder_forward(sd, x, mask, 12)
+    np.testing.assert_allclose(y.norm(dim=-1).numpy(), g["token_norm"][:1], rtol=1e-4)
+
+
+def test_sinusoid_table_matches_reference_formula():
+    """mf:195-205 evaluated literally (python loops) on a small table."""
+    n, d = 7, 10
+    ref = np.array([[p / np.power(10000, 2 * (j // 2) / d) for j in range(d)] for p in range(n)])
+    ref[:, 0::2] = np.sin(ref[:, 0::2])
+    ref[:, 1::2] = np.cos(ref[:, 1::2])
+    got = vit_oracle.sinusoid_table(n, d)
+    assert got.shape == (1, n, d) and got.dtype == torch.float32
+    np.testing.assert_array_equal(got[0].numpy(), ref.astype(np.float32))
+
+
+def test_tube_mask_geometry():
+    """masking_generator.py:3-23: int(ratio*196) masked positions, identical in the 8 temporal slots."""
+    m = synth.tube_mask(3, 0.9, seed=0).reshape(3, 8, 196)
+    assert (m.sum(-1) == int(0.9 * 196)).all()
+    assert (m == m[:, :1]).all()
+    assert vit_oracle.visible_indices(m.reshape(3, -1)).shape == (3, 160)
+    m75 = synth.tube_mask(1, 0.75, seed=1)
+    assert int((~m75).sum()) == 392
+
+
+def test_sliding_window_geometry():
+    """sequencing.py:38-62 / dota.py:204-223: T frames -> T-15 windows of 16 consecutive frames, stride 1."""
+    frames = synth.make_video(20, seed=0)
+    clips = synth.windows_from_video(frames)
+    assert clips.shape == (5, 3, 16, 224, 224)
+    assert torch.equal(clips[2][:, 3], frames[5])  # window 2, slot 3 = frame 5
+    assert torch.equal(clips[4][:, 15], frames[19])  # label frame of the last window = last frame
