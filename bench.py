@@ -1,0 +1,325 @@
+"""Benchmark of the hot path: ViT-B/16 16x224^2 frame-level sliding-window inference (BASELINE.json config 2).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+One "step" = one batch of `--batch` (64) stride-1 windows of a synthetic DoTA-shaped video scored through
+VisionTransformer.forward_windows (fp32->bf16 cast, patch embed, 12 blocks, pool/norm/head): clips/s = windows/s.
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+GFLOP_PER_CLIP = {  # F = 2*N*1536*D + L*(24*N*D^2 + 4*N^2*D), N = 1568
+    "vit_small_patch16_224": 113.76, "vit_base_patch16_224": 360.69, "vit_large_patch16_224": 1193.67,
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="stad", choices=["stad", "reference"])
+    ap.add_argument("--model", default="vit_base_patch16_224", choices=sorted(GFLOP_PER_CLIP))
+    ap.add_argument("--batch", type=int, default=64, help="windows (clips) per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-clips", type=int, default=1, help="--impl reference: clips per step (bounded sample)")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_forward_setup(model_name):
+    """The reference algorithm on the CPU (oracle/ = restatement of modeling_finetune.py pinned by tests/golden)."""
+    from oracle import synth, vit_oracle
+    D, depth, heads = synth.ARCHS[model_name]
+    sd = synth.make_state_dict(model_name, seed=0)
+    torch.set_num_threads(os.cpu_count())
+
+    def run(clips):
+        return vit_oracle.vit_forward(sd, clips, heads)
+    return run, synth
+
+
+def cpu_baseline(model_name, clips=2, repeats=2):
+    run, synth = cpu_forward_setup(model_name)
+    x = synth.make_clips(clips, seed=123)
+    run(x[:1])  # warm-up (thread pool, oneDNN primitives)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        run(x)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": clips / best, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"best of {repeats} fp32 forwards of {clips} synthetic clips ({model_name}) through oracle/vit_oracle.py "
+                      f"(torch {torch.__version__} CPU, {torch.get_num_threads()} threads)"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is pure Python and is not
+    present on the GPU box, so this times oracle/ (its restatement, checked against the reference's outputs in
+    tests/golden).  Rank 0 alone runs it."""
+    if rank != 0:
+        return
+    run, synth = cpu_forward_setup(args.model)
+    x = synth.make_clips(args.ref_clips, seed=123)
+    for _ in range(max(1, min(args.warmup, 2))):
+        run(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(x)
+    dt = time.perf_counter() - t0
+    value = args.ref_clips * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "clips/sec (16x224^2)", "value": value, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} 16x224^2 2-class forward, {args.ref_clips} clip(s) per step on the host CPU",
+                   "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{args.steps} steps x {args.ref_clips} clip(s), oracle/vit_oracle.py fp32, "
+                                   f"{torch.get_num_threads()} threads"},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the sm_100a path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    from functools import partial
+    from oracle import synth  # synthetic weights/inputs only (no oracle compute on the GPU arm)
+    from simple_tad_b200 import _lib, modeling_finetune as mf
+    from simple_tad_b200.runner import SlidingWindowRunner, gather_scores
+
+    D, depth, heads = synth.ARCHS[args.model]
+    model = mf.__dict__[args.model](num_classes=2, all_frames=16, tubelet_size=2, init_scale=1.0,
+                                    final_reduction="fc_norm", use_flash_attn=True)
+    model.load_state_dict(synth.make_state_dict(args.model, seed=0))
+    model = model.to(dev).eval()
+    prep = model.prepare(dev)
+
+    B = args.batch
+    T_frames = B + 15  # B stride-1 windows need B + 15 frames
+    n_bufs = 4         # rotate distinct videos so the inputs of a step are never L2-resident from the step before
+    host_videos = [synth.make_video(T_frames, seed=10 * rank + i).pin_memory() for i in range(n_bufs)]
+    dev_videos = [v.to(dev) for v in host_videos]
+    runner = SlidingWindowRunner(model, batch_windows=B, device=dev)
+    scores = torch.zeros(args.steps * B, 2, dtype=torch.float32, device=dev)
+
+    def step(i, out=None):
+        lg, pr = model.forward_windows(dev_videos[i % n_bufs], start=0, count=B)
+        if out is not None:
+            out[i * B:(i + 1) * B] = pr
+        return lg
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident throughput (`value`)
+    for i in range(args.warmup):
+        step(i)
+    launches_per_step = prep.last_launches + 1  # + the fp32->bf16 cast of the frames
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i, scores)
+    if world > 1:
+        gather_scores(scores, world * scores.shape[0])  # the per-frame score gather (NCCL over NVLink), once
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+
+    # ---------------------------------------------------------------- same steps with per-launch events (roofline)
+    cap = (launches_per_step + 4) * args.steps
+    _lib.profile_enable(cap)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for i in range(args.steps):
+        step(i)
+    p1.record()
+    torch.cuda.synchronize()
+    records = _lib.profile_read(cap)
+    _lib.profile_enable(0)
+    ms_profiled = p0.elapsed_time(p1) / args.steps
+    clocks = sampler.stop()
+
+    by_kind = {}
+    for kind, epi, m, n, k, ms in records:
+        if kind == "gemm":
+            flops = 2.0 * m * n * k
+        elif kind == "attention":
+            flops = 4.0 * m * n * float(k) * k * 64
+        else:
+            flops = 0.0
+        d = by_kind.setdefault(kind, {"ms": 0.0, "flops": 0.0, "launches": 0})
+        d["ms"] += ms
+        d["flops"] += flops
+        d["launches"] += 1
+    peaks = load_peaks()
+    total_kernel_ms = sum(d["ms"] for d in by_kind.values()) or 1.0
+    gemm = by_kind.get("gemm", {"ms": 1.0, "flops": 0.0, "launches": 1})
+    att = by_kind.get("attention", {"ms": 1.0, "flops": 0.0, "launches": 1})
+    gemm_tflops = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
+    att_tflops = att["flops"] / (att["ms"] * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]  # kernels timed inside a long step -> sustained figure
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_kernel (tcgen05, all epilogues)", "achieved": gemm_tflops, "peak": peak,
+        "unit": "TFLOP/s", "frac": gemm_tflops / peak, "traffic": None,
+        "peak_source": peaks["source"] + ", sustained cuBLAS bf16",
+        "launches_per_step": gemm["launches"] / args.steps, "avg_launch_ms": gemm["ms"] / max(1, gemm["launches"]),
+        "share_of_step": gemm["ms"] / total_kernel_ms,
+        "attention": {"achieved": att_tflops, "frac": att_tflops / peak, "share_of_step": att["ms"] / total_kernel_ms,
+                      "avg_launch_ms": att["ms"] / max(1, att["launches"])},
+        "other_share_of_step": {k: v["ms"] / total_kernel_ms for k, v in by_kind.items() if k not in ("gemm", "attention")},
+    }
+
+    # ---------------------------------------------------------------- end to end through the public runner API
+    e2e_steps = max(3, min(args.steps, 10))
+    runner.score_frames(host_videos[0])
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        lg, pr = runner.score_frames(host_videos[i % n_bufs])  # pinned host frames in, host scores out
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = host_videos[0].numel() * host_videos[0].element_size()
+    d2h = 2 * B * 2 * 4
+
+    clips_per_s = world * B * args.steps / (ms_total * 1e-3)
+    model_tflops = clips_per_s / world * GFLOP_PER_CLIP[args.model] / 1e3
+    line = {
+        "metric": "clips/sec (16x224^2 bf16)", "value": clips_per_s, "unit": "clips/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.model} 16x224^2 frame-level sliding-window inference, {B} stride-1 windows "
+                               f"(one {T_frames}-frame DoTA-shaped synthetic video chunk) per step per GPU, 2-class head",
+                   "batch_per_gpu": B, "parallelism": f"clip-sharded x{world}, one score gather",
+                   "l2": f"inputs rotate over {n_bufs} distinct videos; activations per step "
+                         f"({B * 1568 * D * 2 * 5 / 1e6:.0f} MB) exceed the 126 MB L2"},
+        "model_tflops_per_gpu": model_tflops,
+        "model_frac_of_peak": {"measured_sustained": model_tflops / peaks["bf16_tflops_sustained"],
+                               "measured_burst": model_tflops / peaks["bf16_tflops"], "spec_2250": model_tflops / 2250.0},
+        "ms_per_step_profiled": ms_profiled,
+        "roofline": roofline,
+        "clocks": clocks,
+        "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "clips/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "SlidingWindowRunner.score_frames(pinned fp32 frames) -> host (logits, probs)"},
+        "gpu_launches": launches_per_step * args.steps,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.model)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

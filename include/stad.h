@@ -120,6 +120,23 @@ STAD_API int stad_abi_version(void);
 STAD_API int stad_init(int device);
 STAD_API const char* stad_last_error(void);
 
+/* ---- per-launch timing (measurement only) ------------------------------------------------------------------------
+ * When enabled, every kernel the library launches is bracketed by a pair of CUDA events recorded on the launching
+ * stream.  stad_profile_read synchronises on the recorded events and returns one record per launch, in launch order.
+ * Not CUDA-graph capturable; leave disabled (the default) outside benchmarks. */
+enum {
+  STAD_K_CAST = 0, STAD_K_GATHER = 1, STAD_K_GEMM = 2, STAD_K_ATTENTION = 3, STAD_K_ROW_STATS = 4,
+  STAD_K_LAYERNORM = 5, STAD_K_POOL = 6
+};
+typedef struct stad_profile_record {
+  int32_t kind;    /* STAD_K_*                                                        */
+  int32_t epi;     /* GEMM: 1 LN-fold | 2 GELU | 4 residual | 8 pos table | 16 patch-embed (5-D TMA) A operand */
+  int32_t m, n, k; /* GEMM: M, N, K; attention: B, H, S; row kernels: rows, cols, 0  */
+  float ms;        /* device time between the two events                             */
+} stad_profile_record;
+STAD_API int stad_profile_enable(int capacity); /* capacity launches are kept; 0 disables and frees the events */
+STAD_API int stad_profile_read(stad_profile_record* out, int max_records); /* returns #records, resets the log */
+
 /* ---- element / row kernels (HBM-bound) ------------------------------------------------------------------------ */
 /* fp32 -> bf16 cast of a clip batch; stands in for torch.cuda.amp.autocast's input cast (eff:428, te:177). */
 STAD_API int stad_cast_f32_bf16(const float* x, void* y, size_t n, stad_stream_t stream);

@@ -16,7 +16,7 @@ STAD_IN_CLIPS, STAD_IN_FRAMES = 0, 1
 EXPORTS = (
     "stad_abi_version", "stad_init", "stad_last_error", "stad_cast_f32_bf16", "stad_row_stats", "stad_layernorm",
     "stad_pool_norm_head", "stad_patch_embed", "stad_ln_gemm", "stad_gemm_bias_residual", "stad_attention",
-    "stad_workspace_bytes", "stad_vit_forward",
+    "stad_workspace_bytes", "stad_vit_forward", "stad_profile_enable", "stad_profile_read",
 )
 
 
@@ -44,6 +44,13 @@ class StadModel(C.Structure):
 class StadOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("logits", "probs", "features", "tokens")]
 
+
+class StadProfileRecord(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("epi", C.c_int32), ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+                ("ms", C.c_float)]
+
+
+KIND_NAMES = {0: "cast", 1: "gather", 2: "gemm", 3: "attention", 4: "row_stats", 5: "layernorm", 6: "pool"}
 
 _lib = None
 _inited_devices = set()
@@ -73,6 +80,8 @@ def load():
         "stad_gemm_bias_residual": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "stad_attention": (C.c_int, [vp, vp, i32, i32, i32, f32, vp]),
         "stad_workspace_bytes": (sz, [C.POINTER(StadDims), i32, i32]),
+        "stad_profile_enable": (C.c_int, [i32]),
+        "stad_profile_read": (C.c_int, [C.POINTER(StadProfileRecord), i32]),
         "stad_vit_forward": (C.c_int, [C.POINTER(StadModel), C.POINTER(StadInput), vp, i32, i32,
                                        C.POINTER(StadOutputs), vp, sz, vp]),
     }
@@ -110,6 +119,18 @@ def init(device=None):
             check(load().stad_init(idx), "stad_init")
         _inited_devices.add(idx)
     return idx
+
+
+def profile_enable(capacity):
+    """Bracket every library launch with CUDA events (bench.py's per-kernel roofline); 0 disables."""
+    check(load().stad_profile_enable(int(capacity)), "stad_profile_enable")
+
+
+def profile_read(max_records=1 << 16):
+    """[(kind_name, epi, m, n, k, ms)] for every launch since the last read (synchronises on the events)."""
+    buf = (StadProfileRecord * max_records)()
+    n = check(load().stad_profile_read(buf, max_records), "stad_profile_read")
+    return [(KIND_NAMES.get(r.kind, str(r.kind)), r.epi, r.m, r.n, r.k, r.ms) for r in buf[:n]]
 
 
 def stream_ptr():

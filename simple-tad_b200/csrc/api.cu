@@ -172,6 +172,12 @@ int stad_init(int device) {
   return STAD_OK;
 }
 
+int stad_profile_enable(int capacity) { return prof_enable(capacity); }
+int stad_profile_read(stad_profile_record* out, int max_records) {
+  if (out == nullptr || max_records <= 0) return fail(STAD_E_SHAPE, "stad_profile_read: empty output");
+  return prof_read(out, max_records);
+}
+
 int stad_cast_f32_bf16(const float* x, void* y, size_t n, stad_stream_t stream) {
   return launch_cast_f32_bf16(x, static_cast<bf16*>(y), n, as_stream(stream));
 }

@@ -303,6 +303,7 @@ int launch_attention(const bf16* qkv, bf16* out, int B, int H, int S, float scal
   a.S = S;
   a.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(ceil_div(S, BQ), H, B);
+  ProfScope prof(STAD_K_ATTENTION, 0, B, H, S, stream);
   attention_kernel<<<grid, ATT_THREADS, SMEM_BYTES, stream>>>(tm, a);
   STAD_LAUNCH_OK("attention_kernel");
   return STAD_OK;

@@ -44,6 +44,17 @@ int sm_count();  // SMs of the current device (cached)
 int make_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, int swizzle_bytes = 128);
 
+// Per-launch event timing (stad_profile_*). ProfScope records an event pair around one launch when enabled.
+void prof_begin(int kind, int epi, int m, int n, int k, cudaStream_t stream);
+void prof_end(cudaStream_t stream);
+int prof_enable(int capacity);
+int prof_read(stad_profile_record* out, int max_records);
+struct ProfScope {
+  cudaStream_t s;
+  ProfScope(int kind, int epi, int m, int n, int k, cudaStream_t stream) : s(stream) { prof_begin(kind, epi, m, n, k, s); }
+  ~ProfScope() { prof_end(s); }
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace stad

@@ -336,6 +336,7 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& ka, cu
   using C = Cfg<BN>;
   const int tiles = ka.m_tiles * ka.n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
+  ProfScope prof(STAD_K_GEMM, EPI | (kPatch ? 16 : 0), ka.M, ka.N, ka.K, stream);
   gemm_kernel<BN, EPI, kPatch><<<grid, kThreads, C::SMEM_BYTES, stream>>>(ta, tb, ka);
   STAD_LAUNCH_OK("gemm_kernel");
   return STAD_OK;

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 #include <mutex>
+#include <vector>
 
 #include "common.h"
 
@@ -23,6 +24,78 @@ void load_encode() {
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
 }
 }  // namespace
+
+// ---------------------------------------------------------------- per-launch event timing
+namespace {
+struct ProfEntry {
+  stad_profile_record rec;
+  cudaEvent_t e0, e1;
+};
+std::mutex g_prof_mutex;
+std::vector<ProfEntry> g_prof;   // pre-created event pairs
+int g_prof_used = 0;
+bool g_prof_on = false;
+bool g_prof_open = false;        // a begin without its end yet
+}  // namespace
+
+void prof_begin(int kind, int epi, int m, int n, int k, cudaStream_t stream) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  if (g_prof_used >= static_cast<int>(g_prof.size())) return;
+  ProfEntry& e = g_prof[g_prof_used];
+  e.rec.kind = kind;
+  e.rec.epi = epi;
+  e.rec.m = m;
+  e.rec.n = n;
+  e.rec.k = k;
+  e.rec.ms = 0.f;
+  cudaEventRecord(e.e0, stream);
+  g_prof_open = true;
+}
+
+void prof_end(cudaStream_t stream) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  if (!g_prof_open) return;
+  cudaEventRecord(g_prof[g_prof_used].e1, stream);
+  ++g_prof_used;
+  g_prof_open = false;
+}
+
+int prof_enable(int capacity) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  for (auto& e : g_prof) {
+    cudaEventDestroy(e.e0);
+    cudaEventDestroy(e.e1);
+  }
+  g_prof.clear();
+  g_prof_used = 0;
+  g_prof_open = false;
+  g_prof_on = capacity > 0;
+  if (capacity > 0) {
+    g_prof.resize(capacity);
+    for (auto& e : g_prof) {
+      if (cudaEventCreate(&e.e0) != cudaSuccess || cudaEventCreate(&e.e1) != cudaSuccess)
+        return fail(STAD_E_CUDA, "stad_profile_enable: cudaEventCreate failed");
+    }
+  }
+  return STAD_OK;
+}
+
+int prof_read(stad_profile_record* out, int max_records) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  int n = g_prof_used < max_records ? g_prof_used : max_records;
+  for (int i = 0; i < n; ++i) {
+    ProfEntry& e = g_prof[i];
+    if (cudaEventSynchronize(e.e1) != cudaSuccess) return fail(STAD_E_CUDA, "stad_profile_read: event sync failed");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.e0, e.e1);
+    e.rec.ms = ms;
+    out[i] = e.rec;
+  }
+  g_prof_used = 0;
+  return n;
+}
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;

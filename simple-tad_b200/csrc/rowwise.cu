@@ -254,6 +254,7 @@ int launch_cast_f32_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream)
   const size_t cap = static_cast<size_t>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   if (blocks == 0) blocks = 1;
+  ProfScope prof(STAD_K_CAST, 0, static_cast<int>(n >> 10), 1024, 0, stream);
   cast_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x, y, n8, n);
   STAD_LAUNCH_OK("cast_kernel");
   return STAD_OK;
@@ -271,6 +272,7 @@ int launch_row_stats(const bf16* x, float2* stats, int M, int D, float eps, cuda
   int rc = check_row_args(x, M, D);
   if (rc) return rc;
   const int rows_per_block = 8;
+  ProfScope prof(STAD_K_ROW_STATS, 0, M, D, 0, stream);
   row_norm_kernel<false><<<ceil_div(M, rows_per_block), rows_per_block * 32, 0, stream>>>(x, stats, nullptr, nullptr,
                                                                                          nullptr, M, D, eps);
   STAD_LAUNCH_OK("row_stats");
@@ -284,6 +286,7 @@ int launch_layernorm(const bf16* x, const float* g, const float* b, float* y, in
   if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15)
     return fail(STAD_E_ALIGN, "layernorm: g, b, y must be 16-byte aligned");
   const int rows_per_block = 8;
+  ProfScope prof(STAD_K_LAYERNORM, 0, M, D, 0, stream);
   row_norm_kernel<true><<<ceil_div(M, rows_per_block), rows_per_block * 32, 0, stream>>>(x, nullptr, g, b, y, M, D,
                                                                                         eps);
   STAD_LAUNCH_OK("layernorm");
@@ -300,6 +303,7 @@ int launch_pool_norm_head(const bf16* x, const float* g, const float* b, const f
   const int groups = threads / (D >> 3);
   STAD_CHECK_ARG(groups >= 1, "pool_norm_head: D too large for the pooling block");
   const size_t smem1 = static_cast<size_t>(groups) * D * sizeof(float);
+  ProfScope prof(STAD_K_POOL, 0, B * N, D, 0, stream);
   pool_partial_kernel<<<dim3(kPoolChunks, B), threads, smem1, stream>>>(x, scratch, N, D);
   STAD_LAUNCH_OK("pool_partial");
   const size_t smem2 = (static_cast<size_t>(D) + 32 + C) * sizeof(float);
@@ -315,6 +319,7 @@ int launch_gather_patches(const bf16* planes, const PatchGeom& pg, const int32_t
     return fail(STAD_E_ALIGN, "gather_patches: pointers must be 16-byte aligned");
   const size_t total = static_cast<size_t>(B) * n_tok * (K >> 3);
   const int threads = 256;
+  ProfScope prof(STAD_K_GATHER, 0, B * n_tok, K, 0, stream);
   gather_patches_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
       planes, pg, tok_idx, out, B, n_tok, K);
   STAD_LAUNCH_OK("gather_patches");

@@ -1,0 +1,119 @@
+"""Frame-level sliding-window inference (the callers of the hot path): run_inference.py:69-109,
+run_inference_simple.py:428-465 (streaming one video) and engine_for_frame_finetuning.final_test:385-463 with
+utils.gather_predictions_nontensor:791-810 (a dataset of videos sharded across the GPUs of one node).
+
+B200-first differences from the reference, none of which change the scores:
+  * windows are never materialised: frames are uploaded once per video chunk and the patch-embed kernel reads every
+    window straight out of the frame buffer (15/16 of the bytes of consecutive windows are shared);
+  * ranks take CONTIGUOUS blocks of the window index space (DistributedSampler interleaves, rff:311-314), so a rank
+    uploads each frame at most once;
+  * one fixed-size all_gather_into_tensor of fp32 scores replaces the pickle-based all_gather_object (ut:803).
+Clips are independent, so there is no collective on the data path."""
+import math
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, world_size, rank):
+    """Contiguous block of window indices owned by `rank`: (lo, hi, per_rank) with per_rank = ceil(n / world)."""
+    per = max(1, math.ceil(n / max(1, world_size)))
+    lo = min(rank * per, n)
+    hi = min(lo + per, n)
+    return lo, hi, per
+
+
+def gather_scores(local, n_total, group=None):
+    """Every rank contributes its [hi-lo, C] block (padded to per_rank rows); returns the full [n_total, C] tensor on
+    every rank.  Works on CUDA tensors over NCCL (NVLink) and on CPU tensors over gloo (tests)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local[:n_total]
+    world = dist.get_world_size(group)
+    per = max(1, math.ceil(n_total / world))
+    C = local.shape[1]
+    padded = torch.zeros(per, C, dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    out = torch.empty(world * per, C, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return out[:n_total]
+
+
+def window_segments(video_lengths, lo, hi, frames_per_clip=16, stride=1):
+    """Map the global window range [lo, hi) onto (video, first_window, n_windows) segments.
+    A video of T frames has (T - frames_per_clip) // stride + 1 windows (sequencing.py:38-62)."""
+    segs = []
+    base = 0
+    for v, T in enumerate(video_lengths):
+        n = (T - frames_per_clip) // stride + 1 if T >= frames_per_clip else 0
+        a, b = max(lo, base), min(hi, base + n)
+        if a < b:
+            segs.append((v, a - base, b - a))
+        base += n
+    return segs, base
+
+
+class SlidingWindowRunner:
+    """Scores every 16-frame window of one or many videos with a VisionTransformer of this package."""
+
+    def __init__(self, model, batch_windows=64, device=None, stride=1):
+        self.model = model.eval()
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        self.batch_windows = int(batch_windows)
+        self.stride = int(stride)
+        self.T = model.num_frames
+        self._dev_frames = None
+
+    def _upload(self, frames):
+        """Host frames [F, C, H, W] -> reused device buffer (async copy on the current stream if pinned)."""
+        if frames.is_cuda:
+            return frames
+        n = frames.numel()
+        if self._dev_frames is None or self._dev_frames.numel() < n or self._dev_frames.dtype != frames.dtype:
+            self._dev_frames = torch.empty(n, dtype=frames.dtype, device=self.device)
+        dst = self._dev_frames[:n].view(frames.shape)
+        dst.copy_(frames, non_blocking=True)
+        return dst
+
+    @torch.no_grad()
+    def score_frames_device(self, frames):
+        """frames [F, C, H, W] (host or device) -> (logits, probs) [F - T + 1 (strided), num_classes] on the device."""
+        dev = self._upload(frames)
+        F_ = dev.shape[0]
+        n = (F_ - self.T) // self.stride + 1
+        if n < 1:
+            raise ValueError(f"need at least {self.T} frames, got {F_}")
+        logits, probs = [], []
+        for w0 in range(0, n, self.batch_windows):
+            cnt = min(self.batch_windows, n - w0)
+            lg, pr = self.model.forward_windows(dev, start=w0 * self.stride, count=cnt, stride=self.stride)
+            logits.append(lg)
+            probs.append(pr)
+        return (logits[0], probs[0]) if len(logits) == 1 else (torch.cat(logits), torch.cat(probs))
+
+    @torch.no_grad()
+    def score_frames(self, frames):
+        """As above, returning host tensors: the per-frame anomaly probabilities a caller prints (ri:104-108).
+        Window w's score belongs to frame w + T - 1 (label = last frame, dota.py:217-223)."""
+        logits, probs = self.score_frames_device(frames)
+        return logits.cpu(), probs.cpu()
+
+    @torch.no_grad()
+    def score_videos(self, videos, group=None):
+        """videos: list of host frame tensors [T_v, C, H, W].  The global window index space is split into contiguous
+        per-rank blocks; each rank scores its block and ONE gather returns logits [n_windows, num_classes] (same on
+        every rank), ordered video by video, window by window."""
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        lengths = [int(v.shape[0]) for v in videos]
+        _, n_total = window_segments(lengths, 0, 0, self.T, self.stride)
+        lo, hi, per = shard_range(n_total, world, rank)
+        segs, _ = window_segments(lengths, lo, hi, self.T, self.stride)
+        outs = []
+        for v, w0, cnt in segs:
+            f0 = w0 * self.stride
+            f1 = (w0 + cnt - 1) * self.stride + self.T
+            lg, _ = self.score_frames_device(videos[v][f0:f1])
+            outs.append(lg.clone())
+        C = self.model.num_classes
+        local = torch.cat(outs) if outs else torch.zeros(0, C, dtype=torch.float32, device=self.device)
+        return gather_scores(local, n_total, group)

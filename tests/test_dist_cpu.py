@@ -1,0 +1,67 @@
+"""CPU, world_size 2 over gloo: the clip-sharding and score-gather logic of the multi-GPU runner
+(replaces DistributedSampler + gather_predictions_nontensor, rff:311-314 / ut:791-810)."""
+import importlib
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_shard_range_covers_everything_once():
+    from simple_tad_b200.runner import shard_range
+    for n in (0, 1, 7, 85, 680, 681):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                lo, hi, per = shard_range(n, world, r)
+                assert 0 <= lo <= hi <= n and hi - lo <= per
+                seen += list(range(lo, hi))
+            assert seen == list(range(n))
+
+
+def test_window_segments_follow_the_dataset_geometry():
+    from simple_tad_b200.runner import window_segments
+    segs, total = window_segments([100, 20, 15, 16], 0, 10 ** 9)
+    assert total == 85 + 5 + 0 + 1                      # T - 15 windows per video (dota.py:209-223)
+    assert segs == [(0, 0, 85), (1, 0, 5), (3, 0, 1)]
+    segs, _ = window_segments([100, 20, 15, 16], 80, 88)
+    assert segs == [(0, 80, 5), (1, 0, 3)]
+
+
+def _worker(rank, world, port, n_total, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from simple_tad_b200.runner import gather_scores, shard_range
+    lo, hi, per = shard_range(n_total, world, rank)
+    # the score of global window i is (i, -i): any misplacement is visible after the gather
+    local = torch.stack([torch.arange(lo, hi, dtype=torch.float32), -torch.arange(lo, hi, dtype=torch.float32)], 1)
+    full = gather_scores(local, n_total)
+    torch.save(full, os.path.join(tmp, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [85, 680, 7])
+def test_gather_scores_world_size_2_gloo(tmp_path, n_total):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_total, str(tmp_path)), nprocs=world, join=True)
+    want = torch.stack([torch.arange(n_total, dtype=torch.float32), -torch.arange(n_total, dtype=torch.float32)], 1)
+    for r in range(world):
+        got = torch.load(os.path.join(str(tmp_path), f"r{r}.pt"))
+        assert torch.equal(got, want), f"rank {r} gathered a different score table"
