@@ -32,9 +32,12 @@ int make_geom(const stad_dims* d, const stad_input* in, int B, PatchGeom* pg) {
   pg->Tp = d->frames / d->tubelet;
   pg->Hp = d->img_h / 16;
   pg->Wp = d->img_w / 16;
-  const int max_rows = 128 / pg->Wp;                       // h' rows that fit one 128-row MMA tile
-  pg->h_tiles = ceil_div(pg->Hp, max_rows);
-  pg->hp_tile = ceil_div(pg->Hp, pg->h_tiles);             // balanced split (224px: 7 + 7)
+  const int max_rows = 128 / pg->Wp;  // h' rows that fit one 128-row MMA tile
+  int hp_tile = 1;                    // largest divisor of Hp that fits: every tile then holds the same token count
+  for (int d = 1; d <= max_rows && d <= pg->Hp; ++d)
+    if (pg->Hp % d == 0) hp_tile = d;
+  pg->hp_tile = hp_tile;              // 224 px: 7 (98 tokens / tile); 384 px: 4; 512 px: 4
+  pg->h_tiles = pg->Hp / hp_tile;
   pg->C = d->in_chans;
   pg->T = d->frames;
   pg->tubelet = d->tubelet;

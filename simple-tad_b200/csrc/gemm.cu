@@ -3,7 +3,9 @@
 //   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : MMA issuer     (one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128 x N=BN x K=16)
 //                 + TMEM owner   (2 accumulator stages so the epilogue of tile i overlaps the mainloop of tile i+1)
-//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> registers -> bias / LN-fold / GELU / residual / pos -> bf16 -> HBM)
+//   warps 2..9  : epilogue       two warpgroups, each owning half of the BN columns: tcgen05.ld 32x32b -> registers ->
+//                                bias / LN-fold / GELU / pos -> (+ residual sub-tile fetched by TMA into the staging
+//                                buffer) -> bf16 -> 64B-swizzled smem staging -> TMA store (128 rows x 32 columns)
 //
 // Replaces every nn.Linear / F.linear on the reference path (modeling_finetune.py:48,52,92,104,119,128) and, in
 // patch mode, the Conv3d of PatchEmbed (modeling_finetune.py:181-190): the A operand is then fetched with a 5-D tensor
@@ -24,17 +26,21 @@ constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr int kSubCols = 32;                      // columns per epilogue sub-tile = one tcgen05.ld.x32 = one TMA store
+constexpr int kSubTileBytes = BM * kSubCols * 2;  // 8 KB: 128 rows x 64 B, SWIZZLE_64B
 
 template <int BN>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : BN == 192 ? 5 : BN == 128 ? 6 : 8;
+  static constexpr int STAGES = BN == 256 ? 4 : BN == 192 ? 4 : BN == 128 ? 6 : 8;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1024B alignment
+  static constexpr int STAGING_BYTES = 2 * 2 * kSubTileBytes;  // 2 warpgroups x 2 buffers x (128 rows x 64 B)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
 };
 
 struct KArgs {
@@ -78,18 +84,21 @@ STAD_DEVICE TileRows tile_rows(const KArgs& p, int m_tile) {
 
 template <int BN, int EPI, bool kPatch>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const KArgs p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, const KArgs p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles; align in the shared address space.
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;  // [warpgroup][buffer][128 rows x 64 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + C::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full_bar = empty_bar + C::STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* buf_ready_bar = tmem_empty_bar + 2;  // [warpgroup][buffer]: staging buffer free (+ residual landed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_ready_bar + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,6 +108,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    if constexpr (EPI & EPI_RESID) tma_prefetch_desc(&tmap_res);
+    for (int s = 0; s < 4; ++s) mbar_init(&buf_ready_bar[s], 1);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -208,10 +220,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int ew = warp - 2;            // 0..7
-    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
-    const int half = ew >> 2;           // which half of the BN columns
+    const int ew = warp - 2;       // 0..7
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int wg = ew >> 2;        // warpgroup = which half of the BN columns
     constexpr int COLS = BN / 2;
+    constexpr int CHUNKS = COLS / kSubCols;
+    const bool leader = (ew & 3) == 0 && lane == 0;  // issues the TMA traffic of this warpgroup
+    const int r = quarter * 32 + lane;               // accumulator row (TMEM lane) of this thread
+    uint8_t* stage_buf = staging + wg * 2 * kSubTileBytes;
+    uint64_t* ready = buf_ready_bar + wg * 2;
+    // 64-byte swizzle of the staging tile: 16-byte chunk c of row r lives at chunk position c ^ ((r >> 1) & 3)
+    const uint32_t row_off = static_cast<uint32_t>(r) * 64u;
+    const uint32_t swz = (static_cast<uint32_t>(r) >> 1) & 3u;
+
+    // Sub-tile coordinates of running chunk index `ci` of this CTA/warpgroup (tile-major, then column chunk).
+    auto chunk_coords = [&](int ci, int& col, int& row0) -> bool {
+      const int tile = blockIdx.x + (ci / CHUNKS) * gridDim.x;
+      if (tile >= num_tiles) return false;
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile % p.n_tiles;
+      col = n_tile * BN + wg * COLS + (ci % CHUNKS) * kSubCols;
+      row0 = tile_rows<kPatch>(p, m_tile).row0;
+      return true;
+    };
+    // Leader: make staging buffer (ci & 1) usable for chunk ci: the TMA store issued from it two chunks ago must have
+    // finished READING it; then either start fetching the residual sub-tile into it or just mark it free.
+    auto prepare_buffer = [&](int ci) {
+      int col, row0;
+      if (!chunk_coords(ci, col, row0)) return;
+      tma_store_wait_read<1>();
+      uint64_t* bar = &ready[ci & 1];
+      if constexpr (EPI & EPI_RESID) {
+        mbar_arrive_expect_tx(bar, kSubTileBytes);
+        tma_load_2d(stage_buf + (ci & 1) * kSubTileBytes, &tmap_res, bar, col, row0);
+      } else {
+        mbar_arrive(bar);
+      }
+    };
+
+    int ci = 0;
+    if (leader) prepare_buffer(0);
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int m_tile = tile / p.n_tiles;
@@ -219,7 +267,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const TileRows tr = tile_rows<kPatch>(p, m_tile);
-      const int r = quarter * 32 + lane;
       const bool row_ok = r < tr.valid_rows;
       const int row = tr.row0 + r;
 
@@ -241,103 +288,117 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::ACC_STRIDE + half * COLS;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::ACC_STRIDE + wg * COLS;
+      uint32_t v[32];
+      tmem_ld32(taddr, v);
 #pragma unroll 1
-      for (int c0 = 0; c0 < COLS; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c0, v);
-        tmem_ld_wait();
-        const int n0 = n_tile * BN + half * COLS + c0;
-        if (n0 < p.N) {
-          float f[32];
+      for (int c = 0; c < CHUNKS; ++c, ++ci) {
+        tmem_ld_wait32(v);
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if constexpr (EPI & EPI_LN) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (c + 1 < CHUNKS) {
+          tmem_ld32(taddr + (c + 1) * kSubCols, v);  // next chunk streams in under this chunk's math
+        } else {
+          // accumulator stage fully in registers: hand it back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        const int n0 = n_tile * BN + wg * COLS + c * kSubCols;
+        if constexpr (EPI & EPI_LN) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 cs = __ldg(reinterpret_cast<const float4*>(p.colsum + n0 + j));
-              f[j + 0] = rstd * fmaf(-mean, cs.x, f[j + 0]);
-              f[j + 1] = rstd * fmaf(-mean, cs.y, f[j + 1]);
-              f[j + 2] = rstd * fmaf(-mean, cs.z, f[j + 2]);
-              f[j + 3] = rstd * fmaf(-mean, cs.w, f[j + 3]);
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 cs = __ldg(reinterpret_cast<const float4*>(p.colsum + n0 + j));
+            f[j + 0] = rstd * fmaf(-mean, cs.x, f[j + 0]);
+            f[j + 1] = rstd * fmaf(-mean, cs.y, f[j + 1]);
+            f[j + 2] = rstd * fmaf(-mean, cs.z, f[j + 2]);
+            f[j + 3] = rstd * fmaf(-mean, cs.w, f[j + 3]);
           }
-          if (p.bias != nullptr) {
+        }
+        if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              f[j + 0] += bv.x;
-              f[j + 1] += bv.y;
-              f[j + 2] += bv.z;
-              f[j + 3] += bv.w;
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            f[j + 0] += bv.x;
+            f[j + 1] += bv.y;
+            f[j + 2] += bv.z;
+            f[j + 3] += bv.w;
           }
-          if constexpr (EPI & EPI_GELU) {
+        }
+        if constexpr (EPI & EPI_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-          }
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        }
+        if constexpr (EPI & EPI_POS) {
           if (row_ok) {
-            if constexpr (EPI & EPI_POS) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 pv = __ldg(reinterpret_cast<const float4*>(pos_row + n0 + j));
-                f[j + 0] += pv.x;
-                f[j + 1] += pv.y;
-                f[j + 2] += pv.z;
-                f[j + 3] += pv.w;
-              }
-            }
-            const size_t off = static_cast<size_t>(row) * p.N + n0;
-            if constexpr (EPI & EPI_RESID) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 rv = rp[q];
-                f[q * 8 + 0] += bf16_lo(rv.x);
-                f[q * 8 + 1] += bf16_hi(rv.x);
-                f[q * 8 + 2] += bf16_lo(rv.y);
-                f[q * 8 + 3] += bf16_hi(rv.y);
-                f[q * 8 + 4] += bf16_lo(rv.z);
-                f[q * 8 + 5] += bf16_hi(rv.z);
-                f[q * 8 + 6] += bf16_lo(rv.w);
-                f[q * 8 + 7] += bf16_hi(rv.w);
-              }
-            }
-            uint4* op = reinterpret_cast<uint4*>(p.out + off);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = pack_bf16(f[q * 8 + 0], f[q * 8 + 1]);
-              o.y = pack_bf16(f[q * 8 + 2], f[q * 8 + 3]);
-              o.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]);
-              o.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
-              op[q] = o;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 pv = __ldg(reinterpret_cast<const float4*>(pos_row + n0 + j));
+              f[j + 0] += pv.x;
+              f[j + 1] += pv.y;
+              f[j + 2] += pv.z;
+              f[j + 3] += pv.w;
             }
           }
         }
+
+        // staging buffer of this chunk is free (and holds the residual sub-tile, if any)
+        uint8_t* buf = stage_buf + (ci & 1) * kSubTileBytes;
+        mbar_wait(&ready[ci & 1], (ci >> 1) & 1);
+        uint4* my_row = reinterpret_cast<uint4*>(buf + row_off);
+        if constexpr (EPI & EPI_RESID) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 rv = my_row[q ^ swz];
+            f[q * 8 + 0] += bf16_lo(rv.x);
+            f[q * 8 + 1] += bf16_hi(rv.x);
+            f[q * 8 + 2] += bf16_lo(rv.y);
+            f[q * 8 + 3] += bf16_hi(rv.y);
+            f[q * 8 + 4] += bf16_lo(rv.z);
+            f[q * 8 + 5] += bf16_hi(rv.z);
+            f[q * 8 + 6] += bf16_lo(rv.w);
+            f[q * 8 + 7] += bf16_hi(rv.w);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16(f[q * 8 + 0], f[q * 8 + 1]);
+          o.y = pack_bf16(f[q * 8 + 2], f[q * 8 + 3]);
+          o.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]);
+          o.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
+          my_row[q ^ swz] = o;
+        }
+        fence_proxy_async_smem();         // generic-proxy writes -> visible to the TMA (async proxy)
+        named_bar_sync(1 + wg, 128);      // whole sub-tile staged
+        if (leader) {
+          tma_store_2d(&tmap_out, buf, n0, tr.row0);  // rows beyond M (or beyond the box) are clipped by the TMA
+          tma_store_commit();
+          prepare_buffer(ci + 1);
+        }
       }
-      // accumulator stage drained: hand it back to the MMA issuer
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if (leader) tma_store_wait<0>();  // all output tiles of this CTA are in global memory
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
 template <int BN, int EPI, bool kPatch>
-int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& ka, cudaStream_t stream) {
+int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+               const KArgs& ka, cudaStream_t stream) {
   using C = Cfg<BN>;
   const int tiles = ka.m_tiles * ka.n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(STAD_K_GEMM, EPI | (kPatch ? 16 : 0), ka.M, ka.N, ka.K, stream);
-  gemm_kernel<BN, EPI, kPatch><<<grid, kThreads, C::SMEM_BYTES, stream>>>(ta, tb, ka);
+  gemm_kernel<BN, EPI, kPatch><<<grid, kThreads, C::SMEM_BYTES, stream>>>(ta, tb, to, tr, ka);
   STAD_LAUNCH_OK("gemm_kernel");
   return STAD_OK;
 }
@@ -360,12 +421,13 @@ int set_smem_all_bn() {
 }
 
 template <int EPI, bool kPatch>
-int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& ka, cudaStream_t stream) {
+int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                const KArgs& ka, cudaStream_t stream) {
   switch (bn) {
-    case 64: return launch_one<64, EPI, kPatch>(ta, tb, ka, stream);
-    case 128: return launch_one<128, EPI, kPatch>(ta, tb, ka, stream);
-    case 192: return launch_one<192, EPI, kPatch>(ta, tb, ka, stream);
-    case 256: return launch_one<256, EPI, kPatch>(ta, tb, ka, stream);
+    case 64: return launch_one<64, EPI, kPatch>(ta, tb, to, tr, ka, stream);
+    case 128: return launch_one<128, EPI, kPatch>(ta, tb, to, tr, ka, stream);
+    case 192: return launch_one<192, EPI, kPatch>(ta, tb, to, tr, ka, stream);
+    case 256: return launch_one<256, EPI, kPatch>(ta, tb, to, tr, ka, stream);
   }
   return fail(STAD_E_SHAPE, "gemm: no tile width for N");
 }
@@ -420,8 +482,9 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   ka.pos_rows = g.pos_rows;
   ka.out = g.out;
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to, tr;
   int rc;
+  int out_box_rows = BM;
   if (g.patch) {
     const PatchGeom& pg = *g.patch;
     ka.pg = pg;
@@ -432,6 +495,9 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
                                  (uint64_t)pg.img_h * pg.img_w * 2};
     const uint32_t box[5] = {16, (uint32_t)pg.Wp, (uint32_t)pg.hp_tile, 1, 1};
     if ((rc = make_tmap_bf16(&ta, g.a, 5, dims, strides, box, 32))) return rc;
+    // every patch tile holds exactly hp_tile * Wp tokens (make_geom picks hp_tile | Hp): the store box is that tall
+    STAD_CHECK_ARG(pg.Hp % pg.hp_tile == 0, "patch mode: hp_tile=%d must divide Hp=%d", pg.hp_tile, pg.Hp);
+    out_box_rows = pg.hp_tile * pg.Wp;
   } else {
     ka.m_tiles = ceil_div(g.M, BM);
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.M};
@@ -448,16 +514,27 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     if ((rc = make_tmap_bf16(&tb, g.w, 2, dims, strides, box))) return rc;
   }
 
+  {
+    // output (and residual) sub-tiles: 32 columns x out_box_rows rows, 64-byte swizzle
+    const uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.M};
+    const uint64_t strides[1] = {(uint64_t)g.N * 2};
+    const uint32_t box[2] = {kSubCols, (uint32_t)out_box_rows};
+    if ((rc = make_tmap_bf16(&to, g.out, 2, dims, strides, box, 64))) return rc;
+    tr = to;
+    if (g.epi & EPI_RESID)
+      if ((rc = make_tmap_bf16(&tr, g.residual, 2, dims, strides, box, 64))) return rc;
+  }
+
   if (g.patch) {
     STAD_CHECK_ARG(g.epi == EPI_POS, "gemm: patch mode supports only the pos epilogue");
-    return dispatch_bn<EPI_POS, true>(bn, ta, tb, ka, stream);
+    return dispatch_bn<EPI_POS, true>(bn, ta, tb, to, tr, ka, stream);
   }
   switch (g.epi) {
-    case 0: return dispatch_bn<0, false>(bn, ta, tb, ka, stream);
-    case EPI_LN: return dispatch_bn<EPI_LN, false>(bn, ta, tb, ka, stream);
-    case EPI_LN | EPI_GELU: return dispatch_bn<EPI_LN | EPI_GELU, false>(bn, ta, tb, ka, stream);
-    case EPI_RESID: return dispatch_bn<EPI_RESID, false>(bn, ta, tb, ka, stream);
-    case EPI_POS: return dispatch_bn<EPI_POS, false>(bn, ta, tb, ka, stream);
+    case 0: return dispatch_bn<0, false>(bn, ta, tb, to, tr, ka, stream);
+    case EPI_LN: return dispatch_bn<EPI_LN, false>(bn, ta, tb, to, tr, ka, stream);
+    case EPI_LN | EPI_GELU: return dispatch_bn<EPI_LN | EPI_GELU, false>(bn, ta, tb, to, tr, ka, stream);
+    case EPI_RESID: return dispatch_bn<EPI_RESID, false>(bn, ta, tb, to, tr, ka, stream);
+    case EPI_POS: return dispatch_bn<EPI_POS, false>(bn, ta, tb, to, tr, ka, stream);
   }
   return fail(STAD_E_SHAPE, "gemm: unsupported epilogue combination %d", g.epi);
 }

@@ -136,10 +136,13 @@ int make_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t*
                                         (unsigned long long)gstr[i - 1]);
     }
   }
-  if (swizzle_bytes != 128 && swizzle_bytes != 32) return fail(STAD_E_SHAPE, "tensor map: swizzle %d unsupported", swizzle_bytes);
+  if (swizzle_bytes != 128 && swizzle_bytes != 64 && swizzle_bytes != 32)
+    return fail(STAD_E_SHAPE, "tensor map: swizzle %d unsupported", swizzle_bytes);
   if (box[0] * 2 != (uint32_t)swizzle_bytes)
     return fail(STAD_E_SHAPE, "tensor map: inner box (%u B) must equal the swizzle span (%d B)", box[0] * 2, swizzle_bytes);
-  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(gptr), gdim, gstr,
                         bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

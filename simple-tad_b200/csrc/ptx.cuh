@@ -106,6 +106,9 @@ STAD_DEVICE void tma_store_2d(const void* tmap, const void* smem_src, int c0, in
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+STAD_DEVICE void named_bar_sync(uint32_t id, uint32_t threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 STAD_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 STAD_DEVICE void tma_store_wait_read() {
@@ -183,6 +186,17 @@ STAD_DEVICE void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 STAD_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, but with the destination registers of the preceding tcgen05.ld as in/out operands: the compiler cannot
+// schedule a use of them above the wait (the wait itself names no registers).
+STAD_DEVICE void tmem_ld_wait32(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 
 STAD_DEVICE void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
