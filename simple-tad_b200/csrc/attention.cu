@@ -5,15 +5,24 @@
 // packed projection qkv[B, S, 3, H, 64] (the layout FlashAttention.forward takes); output is [B, S, H*64], the
 // layout Attention.proj consumes.  The S x S score matrix never leaves the SM.
 //
-//   CTA = one 128-row query tile of one (b, h).            grid = (ceil(S/128), H, B)
-//   warp 0     : TMA producer: Q once, then K/V tiles (128 keys) through a smem ring
-//   warp 1     : MMA issuer (one thread): S_j = Q K_j^T  -> TMEM (2 buffers);  O += P_j V_j  (P_j read from TMEM)
-//   warps 2..5 : softmax, one query row per thread: tcgen05.ld S_j, online max / sum in registers, exp2,
-//                P_j (bf16) written back over S_j with tcgen05.st; O is rescaled lazily (only when the running
-//                max grew by more than 2^8), and normalised + stored at the end.
+// Persistent kernel, one CTA per SM.  A work unit = TWO 128-row query tiles ("slots") of one (b, h) that share every
+// K/V tile streamed through shared memory (head dim 64 makes the kernel exp-bound, so the two slots also give every
+// SM sub-partition two independent softmax warps to interleave on the MUFU).
+//
+//   warp 0       : TMA producer: Q tiles of the unit, then K and V tiles (128 keys each) through two smem rings
+//   warps 1, 2   : MMA issuers, one thread per slot (warp 1 also owns TMEM).  S = Q K_j^T  (SS, fp32, 128 TMEM columns),
+//                  O += P_j V_j  (A = P from TMEM, B = V as MN-major smem operand).  S, P and O live in separate
+//                  TMEM columns, so Q K_{j+1}^T is issued as soon as the softmax warps have pulled S_j into registers.
+//   warps 4..7   : softmax of slot 0, one query row per thread: tcgen05.ld S_j, row max (FMNMX3), exp2 of
+//   warps 8..11  : softmax of slot 1   s*c - m (FFMA2 + MUFU.EX2; a fixed fraction of the pairs on the FMA pipe with a
+//                  Cody-Waite / degree-3 polynomial), row sum (FADD2), P_j (bf16) -> TMEM by tcgen05.st.
+//                  O is rescaled lazily (only when the running max grew by more than 2^8), by the same thread;
+//                  at the end of the unit the thread normalises its O row and stores it.
+//
+// TMEM (512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512).
 //
 // Roofline: dense BF16 tensor; algorithmic FLOPs = 4 S^2 64 per (b, h).  With head dim 64 the MUFU ex2 rate
-// (one exp per 256 MMA flops) is the practical ceiling (SURVEY §7 "hard parts").
+// (one exp per 256 MMA flops, 16 exp/clk/SM) is the practical ceiling (SURVEY §7 "hard parts").
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -21,19 +30,24 @@ namespace stad {
 
 namespace {
 
-constexpr int HD = 64;        // head dim
-constexpr int BQ = 128;       // query rows per CTA
-constexpr int BKV = 128;      // keys per tile
-constexpr int KV_STAGES = 4;
-constexpr int Q_BYTES = BQ * HD * 2;
-constexpr int K_BYTES = BKV * HD * 2;
-constexpr int STAGE_BYTES = 2 * K_BYTES;  // K tile + V tile
-constexpr int ATT_THREADS = 192;
-constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * STAGE_BYTES + 256 + 1024;
+constexpr int HD = 64;    // head dim
+constexpr int BQ = 128;   // query rows per slot
+constexpr int BKV = 128;  // keys per tile
+constexpr int K_STAGES = 4;
+constexpr int V_STAGES = 4;
+constexpr int TILE_BYTES = BQ * HD * 2;  // 16 KB: every Q / K / V tile
+constexpr int ATT_THREADS = 384;         // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1, 2: softmax slots
+constexpr int SMEM_BYTES = (2 + K_STAGES + V_STAGES) * TILE_BYTES + 512 + 1024;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t S_COL0 = 0;    // S buffer b at columns [b*128, b*128+128); P_j aliases its first 64 columns
-constexpr uint32_t O_COL = 256;   // O accumulator: 64 fp32 columns
+constexpr uint32_t S_COL = 0;    // + slot * 128
+constexpr uint32_t P_COL = 256;  // + slot * 64   (bf16 pairs: column k holds keys 2k, 2k+1)
+constexpr uint32_t O_COL = 384;  // + slot * 64
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+// One pair of every kPolyPeriod pairs takes its exp2 on the FMA pipe instead of the MUFU (0 = never).
+#ifndef STAD_ATT_POLY_PERIOD
+#define STAD_ATT_POLY_PERIOD 4
+#endif
+constexpr int kPolyPeriod = STAD_ATT_POLY_PERIOD;
 
 struct AttArgs {
   bf16* out;
@@ -41,41 +55,137 @@ struct AttArgs {
   float scale_log2;  // softmax scale * log2(e)
 };
 
+struct Unit {
+  int b, h, q0, slots;
+};
+
+STAD_DEVICE Unit decode_unit(int u, int units_per_head, int H, int S) {
+  Unit w;
+  const int bh = u / units_per_head;
+  const int t = u - bh * units_per_head;
+  w.b = bh / H;
+  w.h = bh - w.b * H;
+  w.q0 = t * 2 * BQ;
+  w.slots = (w.q0 + BQ < S) ? 2 : 1;
+  return w;
+}
+
+STAD_DEVICE float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// packed two-lane fp32 math (FFMA2 / FADD2)
+STAD_DEVICE void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+STAD_DEVICE void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+STAD_DEVICE float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 2^x for a pair, entirely on the FMA/ALU pipes: x = n + f, n = round(x), f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far below bf16 resolution of P), n added to the
+// exponent field.  x is clamped at -125 so the exponent never wraps.
+STAD_DEVICE void exp2_poly2(float& e0, float& e1, float x0, float x1) {
+  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: x + kMagic holds round(x) in its low mantissa bits
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  float r0, r1, n0, n1, f0, f1, p0, p1;
+  add2(r0, r1, x0, x1, kMagic, kMagic);
+  add2(n0, n1, r0, r1, -kMagic, -kMagic);
+  fma2(f0, f1, n0, n1, -1.f, -1.f, x0, x1);
+  fma2(p0, p1, f0, f1, 0.05517164245247841f, 0.05517164245247841f, 0.2426111400127411f, 0.2426111400127411f);
+  fma2(p0, p1, p0, p1, f0, f1, 0.6932609677314758f, 0.6932609677314758f);
+  fma2(p0, p1, p0, p1, f0, f1, 0.9999280571937561f, 0.9999280571937561f);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
+
+// exp2(s * c - m) of one 32-column chunk of a score row -> 16 packed bf16 pairs; adds the fp32 row sum into acc.
+template <bool kPoly>
+STAD_DEVICE void exp_chunk(const uint32_t (&s)[32], float c, float neg_m, float& acc0, float& acc1,
+                           uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float x0, x1, e0, e1;
+    fma2(x0, x1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), c, c, neg_m, neg_m);
+    if (kPoly && kPolyPeriod > 0 && (i % (kPolyPeriod > 0 ? kPolyPeriod : 1)) == (kPolyPeriod - 1)) {
+      exp2_poly2(e0, e1, x0, x1);
+    } else {
+      e0 = ex2(x0);
+      e1 = ex2(x1);
+    }
+    add2(acc0, acc1, acc0, acc1, e0, e1);
+    pk[i] = pack_bf16(e0, e1);
+  }
+}
+
+STAD_DEVICE float chunk_max(const uint32_t (&s)[32]) {
+  float m = max3(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]));
+#pragma unroll
+  for (int i = 3; i < 31; i += 2) m = max3(m, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+  return fmaxf(m, __uint_as_float(s[31]));
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* smem_q = smem;
-  uint8_t* smem_kv = smem + Q_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + KV_STAGES * STAGE_BYTES);
-  uint64_t* q_full = bars;                       // 1
-  uint64_t* kv_full = bars + 1;                  // KV_STAGES
-  uint64_t* kv_empty = kv_full + KV_STAGES;      // KV_STAGES
-  uint64_t* s_full = kv_empty + KV_STAGES;       // 2
-  uint64_t* p_full = s_full + 2;                 // 2
-  uint64_t* o_full = p_full + 2;                 // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint8_t* smem_q = smem;                                   // [2][16 KB]
+  uint8_t* smem_k = smem_q + 2 * TILE_BYTES;                // [K_STAGES][16 KB]
+  uint8_t* smem_v = smem_k + K_STAGES * TILE_BYTES;         // [V_STAGES][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + V_STAGES * TILE_BYTES);
+  uint64_t* q_full = bars;                   // [2]  TMA -> MMA
+  uint64_t* q_free = q_full + 2;             // [2]  MMA (last Q K^T of the unit) -> TMA
+  uint64_t* k_full = q_free + 2;             // [K_STAGES]
+  uint64_t* k_free = k_full + K_STAGES;      // [K_STAGES]
+  uint64_t* v_full = k_free + K_STAGES;      // [V_STAGES]
+  uint64_t* v_free = v_full + V_STAGES;      // [V_STAGES]
+  uint64_t* s_full = v_free + V_STAGES;      // [2]  MMA -> softmax: S_j complete
+  uint64_t* s_free = s_full + 2;             // [2]  softmax (4 warps) -> MMA: S_j is in registers
+  uint64_t* p_full = s_free + 2;             // [2]  softmax (4 warps) -> MMA: P_j stored
+  uint64_t* o_full = p_full + 2;             // [2]  MMA -> softmax: P_j V_j complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
+  const int n_q = (p.S + BQ - 1) / BQ;
+  const int units_per_head = (n_q + 1) / 2;
+  const int total_units = p.B * p.H * units_per_head;
   const int n_kv = (p.S + BKV - 1) / BKV;
+  const int last_valid = p.S - (n_kv - 1) * BKV;   // valid keys of the last K/V tile, 1..128
+  const int last_chunks = (last_valid + 31) >> 5;  // 32-column chunks of the last tile that hold any valid key
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_free[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 4);  // one arrive per softmax warp
+      mbar_init(&s_free[s], 4);  // one arrive per softmax warp
+      mbar_init(&p_full[s], 4);
+      mbar_init(&o_full[s], 1);
     }
-    mbar_init(o_full, 1);
+    for (int s = 0; s < K_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_free[s], 2);  // one arrive per slot
+    }
+    for (int s = 0; s < V_STAGES; ++s) {
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_free[s], 2);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -87,182 +197,307 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const int col_q = h * HD;
-      const int col_k = (p.H + h) * HD;
-      const int col_v = (2 * p.H + h) * HD;
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-      tma_load_3d(smem_q, &tmap_qkv, q_full, col_q, q0, b);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* sk = smem_kv + stage * STAGE_BYTES;
-        mbar_arrive_expect_tx(&kv_full[stage], STAGE_BYTES);
-        tma_load_3d(sk, &tmap_qkv, &kv_full[stage], col_k, j * BKV, b);
-        tma_load_3d(sk + K_BYTES, &tmap_qkv, &kv_full[stage], col_v, j * BKV, b);
-        if (++stage == KV_STAGES) {
-          stage = 0;
-          phase ^= 1;
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (warp == 0 && lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      uint32_t kst = 0, kph = 0, vst = 0, vph = 0;
+      uint32_t ucnt0 = 0, ucnt1 = 0;  // units started per slot (phase of q_full / q_free)
+      auto load_k = [&](int j, int b, int col_k) {
+        mbar_wait(&k_free[kst], kph ^ 1);
+        mbar_arrive_expect_tx(&k_full[kst], TILE_BYTES);
+        tma_load_3d(smem_k + kst * TILE_BYTES, &tmap_qkv, &k_full[kst], col_k, j * BKV, b);
+        if (++kst == K_STAGES) {
+          kst = 0;
+          kph ^= 1;
         }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major (head dim contiguous)
-      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);   // P from TMEM (K-major), V MN-major (d contiguous)
-      const uint64_t desc_q = make_smem_desc_sw128(smem_u32(smem_q), 16, 1024);
-      const uint32_t tmem_o = tmem_base + O_COL;
-
-      auto issue_qk = [&](int j, int stage) {
-        const uint64_t desc_k = make_smem_desc_sw128(smem_u32(smem_kv + stage * STAGE_BYTES), 16, 1024);
-        const uint32_t tmem_s = tmem_base + S_COL0 + (j & 1) * BKV;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc_qk, k != 0);
-        umma_commit(&s_full[j & 1]);
       };
-
-      mbar_wait(q_full, 0);
-      int stage_qk = 0;  // ring position of the next K tile to multiply
-      uint32_t phase_qk = 0;
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      stage_qk = 1 % KV_STAGES;
-      if (stage_qk == 0) phase_qk ^= 1;
-
-      int stage_pv = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) {
-          mbar_wait(&kv_full[stage_qk], phase_qk);
-          tc_fence_after();
-          issue_qk(j + 1, stage_qk);
-          if (++stage_qk == KV_STAGES) {
-            stage_qk = 0;
-            phase_qk ^= 1;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const Unit w = decode_unit(u, units_per_head, p.H, p.S);
+        const int col_q = w.h * HD;
+        const int col_k = (p.H + w.h) * HD;
+        const int col_v = (2 * p.H + w.h) * HD;
+        mbar_wait(&q_free[0], (ucnt0 & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[0], TILE_BYTES);
+        tma_load_3d(smem_q, &tmap_qkv, &q_full[0], col_q, w.q0, w.b);
+        ++ucnt0;
+        if (w.slots > 1) {
+          mbar_wait(&q_free[1], (ucnt1 & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[1], TILE_BYTES);
+          tma_load_3d(smem_q + TILE_BYTES, &tmap_qkv, &q_full[1], col_q, w.q0 + BQ, w.b);
+          ++ucnt1;
+        }
+        load_k(0, w.b, col_k);
+        for (int j = 0; j < n_kv; ++j) {
+          if (j + 1 < n_kv) load_k(j + 1, w.b, col_k);
+          mbar_wait(&v_free[vst], vph ^ 1);
+          mbar_arrive_expect_tx(&v_full[vst], TILE_BYTES);
+          tma_load_3d(smem_v + vst * TILE_BYTES, &tmap_qkv, &v_full[vst], col_v, j * BKV, w.b);
+          if (++vst == V_STAGES) {
+            vst = 0;
+            vph ^= 1;
           }
         }
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        tc_fence_after();
-        // V tile: 128 keys x 64 d, one 128-byte row per key -> MN-major B operand; 16 keys = 2 x 1024 B per MMA
-        const uint64_t desc_v = make_smem_desc_sw128(smem_u32(smem_kv + stage_pv * STAGE_BYTES + K_BYTES), 0, 1024);
-        const uint32_t tmem_p = tmem_base + S_COL0 + (j & 1) * BKV;
+      }
+    } else if ((warp == 1 || warp == 2) && lane == 0) {
+      // ---------------------------------------------------------------- MMA issuers: warp 1 -> slot 0, warp 2 -> slot 1
+      // One issuing thread per slot keeps the two slots independent: neither ever waits behind a barrier of the other.
+      // Both read the same K / V ring stages; a stage is released by two arrivals (one per slot; in a one-slot unit
+      // the slot-0 thread commits twice).
+      const int slot = warp - 1;
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);  // P from TMEM (K-major), V MN-major (d contiguous)
+      const uint64_t desc_q = make_smem_desc_sw128(smem_u32(smem_q + slot * TILE_BYTES), 16, 1024);
+      const uint32_t tmem_s = tmem_base + S_COL + slot * BKV;
+      const uint32_t tmem_p = tmem_base + P_COL + slot * (BKV / 2);
+      const uint32_t tmem_o = tmem_base + O_COL + slot * HD;
+      uint32_t kc = 0, vc = 0;  // K / V tiles consumed so far (ring position = count % stages)
+      uint32_t g = 0;           // softmax iterations completed by this slot (phase of s_full/s_free/p_full/o_full)
+      uint32_t ucnt = 0;        // units started by this slot (phase of q_full / q_free)
+
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const Unit w = decode_unit(u, units_per_head, p.H, p.S);
+        if (slot >= w.slots) {  // one-slot unit: slot 1 sits it out but stays in step with the rings
+          kc += n_kv;
+          vc += n_kv;
+          continue;
+        }
+        const bool solo = w.slots == 1;
+        // S = Q K^T over the first `cols` keys of the next K tile; releases the K stage
+        auto issue_qk = [&](int cols, bool last_of_unit) {
+          const uint32_t kst = kc % K_STAGES;
+          mbar_wait(&k_full[kst], (kc / K_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t idesc = make_idesc_bf16(BQ, static_cast<uint32_t>(cols), 0, 0);  // Q, K both K-major
+          const uint64_t desc_k = make_smem_desc_sw128(smem_u32(smem_k + kst * TILE_BYTES), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)
-          umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, (j | k) != 0);
-        umma_commit(&kv_empty[stage_pv]);
-        umma_commit(o_full);
-        if (++stage_pv == KV_STAGES) stage_pv = 0;
+          for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc, k != 0);
+          umma_commit(&s_full[slot]);
+          if (last_of_unit) umma_commit(&q_free[slot]);
+          umma_commit(&k_free[kst]);
+          if (solo) umma_commit(&k_free[kst]);
+          ++kc;
+        };
+        // O (+)= P V over the first 16 * ksteps keys.  V tile: one 128-byte row per key -> MN-major B operand;
+        // 16 keys = 2 x 1024 B per MMA.  Releases the V stage.
+        auto issue_pv = [&](bool accumulate, int ksteps) {
+          const uint32_t vst = vc % V_STAGES;
+          mbar_wait(&v_full[vst], (vc / V_STAGES) & 1);
+          tc_fence_after();
+          const uint64_t desc_v = make_smem_desc_sw128(smem_u32(smem_v + vst * TILE_BYTES), 0, 1024);
+          for (int k = 0; k < ksteps; ++k)
+            umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+          umma_commit(&o_full[slot]);
+          umma_commit(&v_free[vst]);
+          if (solo) umma_commit(&v_free[vst]);
+          ++vc;
+        };
+
+        mbar_wait(&q_full[slot], ucnt & 1);
+        if (g > 0) mbar_wait(&s_free[slot], (g - 1) & 1);  // previous S of the slot has been pulled out of TMEM
+        issue_qk(n_kv == 1 ? last_chunks * 32 : BKV, n_kv == 1);
+        for (int j = 0; j < n_kv; ++j) {
+          const bool has_next = j + 1 < n_kv;
+          const bool next_last = j + 2 == n_kv;
+          if (has_next) {
+            mbar_wait(&s_free[slot], (g + j) & 1);
+            issue_qk(next_last ? last_chunks * 32 : BKV, next_last);
+          }
+          mbar_wait(&p_full[slot], (g + j) & 1);
+          issue_pv(j != 0, has_next ? BKV / 16 : last_chunks * 2);
+        }
+        g += n_kv;
+        ++ucnt;
       }
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------------------------------------------ softmax warps (one query row per thread)
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;  // row inside the tile
+    const int slot = (warp - 4) >> 2;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t s_addr = lane_addr + S_COL + slot * BKV;
+    const uint32_t p_addr = lane_addr + P_COL + slot * (BKV / 2);
+    const uint32_t o_addr = lane_addr + O_COL + slot * HD;
     const float c = p.scale_log2;
-    float m_ref = 0.f;  // reference max (log2 domain, already scaled)
-    float l_sum = 0.f;
+    uint32_t g = 0;  // iterations completed by this slot
 
-    for (int j = 0; j < n_kv; ++j) {
-      const uint32_t s_addr = lane_addr + S_COL0 + (j & 1) * BKV;
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t sv[4][32];
-      tmem_ld32(s_addr + 0, sv[0]);
-      tmem_ld32(s_addr + 32, sv[1]);
-      tmem_ld32(s_addr + 64, sv[2]);
-      tmem_ld32(s_addr + 96, sv[3]);
-      tmem_ld_wait();
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const Unit w = decode_unit(u, units_per_head, p.H, p.S);
+      if (slot >= w.slots) continue;
+      const int row0 = w.q0 + slot * BQ;
+      const bool warp_valid = row0 + quarter * 32 < p.S;  // warp-uniform: any valid query row in this warp
+      float m_ref = 0.f;  // reference max (log2 domain, already scaled)
+      float l_sum = 0.f;
 
-      const int kv_valid = p.S - j * BKV;  // >= 1
-      if (kv_valid < BKV) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (q * 32 + i >= kv_valid) sv[q][i] = 0xFF800000u;  // -inf
-      }
-
-      float mx = -INFINITY;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[q][i]));
-      mx *= c;
-
-      if (j == 0) {
-        m_ref = mx;
-      } else {
-        // O and l_sum are relative to m_ref; only move the reference when the max grew by > 2^8 (keeps P <= 256)
-        const bool grow = mx > m_ref + kRescaleThreshold;
-        mbar_wait(o_full, (j - 1) & 1);  // PV(j-1) finished: O is stable, P(j-1) consumed
+      for (int j = 0; j < n_kv; ++j, ++g) {
+        mbar_wait(&s_full[slot], g & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, grow)) {
-          const float alpha = grow ? fast_exp2(m_ref - mx) : 1.0f;
-          if (grow) {
-            m_ref = mx;
-            l_sum *= alpha;
+        if (!warp_valid) {
+          // rows beyond S: nothing to compute (their P / O rows are never stored); keep the pipeline moving.
+          // The p_full arrival must not overtake phase j-1 of that barrier (the computing warps may still be
+          // working on P_{j-1}); P V_{j-1} done implies p_full phase j-1 has completed.
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&s_free[slot]);
+            if (j > 0) mbar_wait(&o_full[slot], (g - 1) & 1);
+            mbar_arrive(&p_full[slot]);
           }
-          uint32_t ov[2][32];
-          tmem_ld32(lane_addr + O_COL, ov[0]);
-          tmem_ld32(lane_addr + O_COL + 32, ov[1]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ov[q][i] = __float_as_uint(__uint_as_float(ov[q][i]) * alpha);
-          tmem_st32(lane_addr + O_COL, ov[0]);
-          tmem_st32(lane_addr + O_COL + 32, ov[1]);
+          continue;
         }
+        const bool full_tile = (j + 1 < n_kv) || last_valid == BKV;
+        if (full_tile) {
+          uint32_t sv[4][32];
+          tmem_ld32(s_addr + 0, sv[0]);
+          tmem_ld32(s_addr + 32, sv[1]);
+          tmem_ld32(s_addr + 64, sv[2]);
+          tmem_ld32(s_addr + 96, sv[3]);
+          tmem_ld_wait32(sv[0]);
+          tmem_ld_wait32(sv[1]);
+          tmem_ld_wait32(sv[2]);
+          tmem_ld_wait32(sv[3]);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[slot]);  // S_j is in registers: Q K_{j+1}^T may overwrite it
+
+          const float mx = c * max3(fmaxf(chunk_max(sv[0]), chunk_max(sv[1])), chunk_max(sv[2]), chunk_max(sv[3]));
+          bool pv_done = (j == 0);  // P V of the previous iteration finished (P buffer reusable, O stable)
+          if (j == 0) {
+            m_ref = mx;
+          } else {
+            // O and l_sum are relative to m_ref; only move the reference when the max grew by > 2^8 (keeps P <= 256)
+            const bool grow = mx > m_ref + kRescaleThreshold;
+            if (__any_sync(0xffffffffu, grow)) {
+              mbar_wait(&o_full[slot], (g - 1) & 1);
+              tc_fence_after();
+              pv_done = true;
+              const float alpha = grow ? ex2(m_ref - mx) : 1.0f;
+              if (grow) {
+                m_ref = mx;
+                l_sum *= alpha;
+              }
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                uint32_t ov[32];
+                tmem_ld32(o_addr + q * 32, ov);
+                tmem_ld_wait32(ov);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                tmem_st32(o_addr + q * 32, ov);
+              }
+            }
+          }
+          const float neg_m = -m_ref;
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t pk[16];
+            if (q & 1) exp_chunk<true>(sv[q], c, neg_m, b0, b1, pk);
+            else exp_chunk<true>(sv[q], c, neg_m, a0, a1, pk);
+            if (q == 0 && !pv_done) {
+              mbar_wait(&o_full[slot], (g - 1) & 1);  // P V_{j-1} has consumed the P buffer
+              tc_fence_after();
+            }
+            tmem_st16(p_addr + q * 16, pk);
+          }
+          l_sum += (a0 + a1) + (b0 + b1);
+        } else {
+          // ---- last K/V tile with fewer than 128 valid keys: chunk loop, S read twice (max pass, exp pass)
+          float rmax = -INFINITY;
+#pragma unroll 1
+          for (int q = 0; q < last_chunks; ++q) {
+            uint32_t t[32];
+            tmem_ld32(s_addr + q * 32, t);
+            tmem_ld_wait32(t);
+            const int valid = last_valid - q * 32;
+            if (valid < 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i >= valid) t[i] = 0xFF800000u;  // -inf
+            }
+            rmax = fmaxf(rmax, chunk_max(t));
+          }
+          const float mx = c * rmax;
+          bool pv_done = (j == 0);
+          if (j == 0) {
+            m_ref = mx;
+          } else {
+            const bool grow = mx > m_ref + kRescaleThreshold;
+            if (__any_sync(0xffffffffu, grow)) {
+              mbar_wait(&o_full[slot], (g - 1) & 1);
+              tc_fence_after();
+              pv_done = true;
+              const float alpha = grow ? ex2(m_ref - mx) : 1.0f;
+              if (grow) {
+                m_ref = mx;
+                l_sum *= alpha;
+              }
+#pragma unroll 1
+              for (int q = 0; q < 2; ++q) {
+                uint32_t ov[32];
+                tmem_ld32(o_addr + q * 32, ov);
+                tmem_ld_wait32(ov);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                tmem_st32(o_addr + q * 32, ov);
+              }
+            }
+          }
+          if (!pv_done) {
+            mbar_wait(&o_full[slot], (g - 1) & 1);
+            tc_fence_after();
+          }
+          const float neg_m = -m_ref;
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll 1
+          for (int q = 0; q < last_chunks; ++q) {
+            uint32_t t[32];
+            tmem_ld32(s_addr + q * 32, t);
+            tmem_ld_wait32(t);
+            const int valid = last_valid - q * 32;
+            if (valid < 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i >= valid) t[i] = 0xFF800000u;
+            }
+            uint32_t pk[16];
+            exp_chunk<false>(t, c, neg_m, a0, a1, pk);
+            tmem_st16(p_addr + q * 16, pk);
+          }
+          l_sum += a0 + a1;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[slot]);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[slot]);
       }
 
-      // P = exp2(s*c - m_ref), packed to bf16 pairs: TMEM column k of P holds keys (2k, 2k+1)
-      uint32_t pk[2][32];
-      float sum = 0.f;
+      // ---- finalise: O / l  -> bf16 -> out[b, row0 + r, h*64 .. h*64+63]
+      if (warp_valid) {
+        mbar_wait(&o_full[slot], (g - 1) & 1);
+        tc_fence_after();
+        const int row = row0 + r;
+        const float inv = 1.0f / l_sum;
+        uint4* op = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(w.b) * p.S + row) * (p.H * HD) + w.h * HD);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
+          uint32_t ov[32];
+          tmem_ld32(o_addr + q * 32, ov);
+          tmem_ld_wait32(ov);
+          if (row < p.S) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(sv[q][i]), c, -m_ref));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(sv[q][i + 1]), c, -m_ref));
-          sum += e0 + e1;
-          pk[q >> 1][(q & 1) * 16 + (i >> 1)] = pack_bf16(e0, e1);
-        }
-      }
-      l_sum += sum;
-      tmem_st32(s_addr, pk[0]);
-      tmem_st32(s_addr + 32, pk[1]);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[j & 1]);
-    }
-
-    // ---- finalise: O / l  -> bf16 -> out[b, q0 + r, h*64 .. h*64+63]
-    mbar_wait(o_full, (n_kv - 1) & 1);
-    tc_fence_after();
-    uint32_t ov[2][32];
-    tmem_ld32(lane_addr + O_COL, ov[0]);
-    tmem_ld32(lane_addr + O_COL + 32, ov[1]);
-    tmem_ld_wait();
-    const int row = q0 + r;
-    if (row < p.S) {
-      const float inv = 1.0f / l_sum;
-      uint4* op = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(b) * p.S + row) * (p.H * HD) + h * HD);
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(ov[q][i + 0]) * inv, __uint_as_float(ov[q][i + 1]) * inv);
-          o.y = pack_bf16(__uint_as_float(ov[q][i + 2]) * inv, __uint_as_float(ov[q][i + 3]) * inv);
-          o.z = pack_bf16(__uint_as_float(ov[q][i + 4]) * inv, __uint_as_float(ov[q][i + 5]) * inv);
-          o.w = pack_bf16(__uint_as_float(ov[q][i + 6]) * inv, __uint_as_float(ov[q][i + 7]) * inv);
-          op[q * 4 + (i >> 3)] = o;
+            for (int i = 0; i < 32; i += 8) {
+              uint4 o;
+              o.x = pack_bf16(__uint_as_float(ov[i + 0]) * inv, __uint_as_float(ov[i + 1]) * inv);
+              o.y = pack_bf16(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+              o.z = pack_bf16(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+              o.w = pack_bf16(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+              op[q * 4 + (i >> 3)] = o;
+            }
+          }
         }
       }
     }
@@ -286,7 +521,6 @@ int attention_init() {
 
 int launch_attention(const bf16* qkv, bf16* out, int B, int H, int S, float scale, cudaStream_t stream) {
   STAD_CHECK_ARG(B > 0 && H > 0 && S > 0, "attention: empty problem B=%d H=%d S=%d", B, H, S);
-  STAD_CHECK_ARG(B <= 65535 && H <= 65535, "attention: B=%d / H=%d exceed the grid limits", B, H);
   if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) & 15)
     return fail(STAD_E_ALIGN, "attention: qkv and out must be 16-byte aligned");
   const uint64_t row = static_cast<uint64_t>(3) * H * HD;  // elements per token in the packed projection
@@ -302,7 +536,10 @@ int launch_attention(const bf16* qkv, bf16* out, int B, int H, int S, float scal
   a.H = H;
   a.S = S;
   a.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid(ceil_div(S, BQ), H, B);
+  const int n_q = ceil_div(S, BQ);
+  const long long total_units = static_cast<long long>(B) * H * ((n_q + 1) / 2);
+  STAD_CHECK_ARG(total_units < (1ll << 30), "attention: B*H*tiles = %lld too large", total_units);
+  const int grid = total_units < sm_count() ? static_cast<int>(total_units) : sm_count();
   ProfScope prof(STAD_K_ATTENTION, 0, B, H, S, stream);
   attention_kernel<<<grid, ATT_THREADS, SMEM_BYTES, stream>>>(tm, a);
   STAD_LAUNCH_OK("attention_kernel");

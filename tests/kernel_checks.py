@@ -200,6 +200,13 @@ CHECKS = {
     "attention_small": lambda: check_attention(1, 1, 128),
     "attention_tail": lambda: [check_attention(1, 2, 160), check_attention(2, 1, 392)],
     "attention": lambda: [check_attention(2, 3, 1568), check_attention(1, 12, 1568, peaky=6.0)],
+    # ragged shapes: a single K/V tile, 1-key / 127-key tails, one- and two-slot units, query tails in every warp
+    "attention_ragged": lambda: [check_attention(1, 1, 32), check_attention(2, 2, 100), check_attention(1, 2, 129),
+                                 check_attention(1, 1, 255), check_attention(2, 1, 257), check_attention(1, 3, 300),
+                                 check_attention(1, 2, 640, peaky=4.0)],
+    # more work units than SMs: every CTA of the persistent kernel loops over several units (phase bookkeeping)
+    "attention_persistent": lambda: [check_attention(5, 12, 1568, seed=3), check_attention(40, 12, 160, seed=4),
+                                     check_attention(16, 6, 392, peaky=5.0, seed=5)],
     "patch_embed": lambda: [check_patch_embed(2, 384, "clips"), check_patch_embed(3, 768, "clips")],
     "patch_embed_frames": lambda: check_patch_embed(3, 384, "frames"),
     "patch_embed_masked": lambda: [check_patch_embed(2, 768, "clips", masked=True),
