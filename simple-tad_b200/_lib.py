@@ -7,7 +7,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstad.so")
+LIB_PATH = os.environ.get("STAD_LIB") or os.path.join(_HERE, "libstad.so")  # STAD_LIB: development A/B builds
 
 STAD_OK, STAD_E_SHAPE, STAD_E_ALIGN, STAD_E_ARCH, STAD_E_CUDA = 0, -1, -2, -3, -4
 STAD_EPI_BIAS, STAD_EPI_BIAS_GELU = 0, 1

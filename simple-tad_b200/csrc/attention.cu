@@ -9,15 +9,17 @@
 // K/V tile streamed through shared memory (head dim 64 makes the kernel exp-bound, so the two slots also give every
 // SM sub-partition two independent softmax warps to interleave on the MUFU).
 //
-//   warp 0       : TMA producer: Q tiles of the unit, then K and V tiles (128 keys each) through two smem rings
-//   warps 1, 2   : MMA issuers, one thread per slot (warp 1 also owns TMEM).  S = Q K_j^T  (SS, fp32, 128 TMEM columns),
+//   warp 12      : TMA producer: Q tiles of the unit, then K and V tiles (128 keys each) through two smem rings
+//   warps 13, 14 : MMA issuers, one thread per slot (warp 1 also owns TMEM).  S = Q K_j^T  (SS, fp32, 128 TMEM columns),
 //                  O += P_j V_j  (A = P from TMEM, B = V as MN-major smem operand).  S, P and O live in separate
 //                  TMEM columns, so Q K_{j+1}^T is issued as soon as the softmax warps have pulled S_j into registers.
-//   warps 4..7   : softmax of slot 0, one query row per thread: tcgen05.ld S_j, row max (FMNMX3), exp2 of
-//   warps 8..11  : softmax of slot 1   s*c - m (FFMA2 + MUFU.EX2; a fixed fraction of the pairs on the FMA pipe with a
+//   warps 0..3   : softmax of slot 0, one query row per thread: tcgen05.ld S_j, row max (FMNMX3), exp2 of
+//   warps 4..7   : softmax of slot 1   s*c - m (FFMA2 + MUFU.EX2; a fixed fraction of the pairs on the FMA pipe with a
 //                  Cody-Waite / degree-3 polynomial), row sum (FADD2), P_j (bf16) -> TMEM by tcgen05.st.
-//                  O is rescaled lazily (only when the running max grew by more than 2^8), by the same thread;
-//                  at the end of the unit the thread normalises its O row and stores it.
+//                  O is rescaled lazily (only when the running max grew by more than 2^8), by the same thread.
+//                  The loop is software-pipelined: S_{j+1} is pulled into registers while the P_j stores drain.
+//   warps 8..11  : epilogue: at the end of a unit they take the row sums from the softmax warps, read O, normalise
+//                  and store it, so the softmax warps start the next unit immediately.
 //
 // TMEM (512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512).
 //
@@ -25,6 +27,7 @@
 // (one exp per 256 MMA flops, 16 exp/clk/SM) is the practical ceiling (SURVEY §7 "hard parts").
 #include "kernels.h"
 #include "ptx.cuh"
+#include "softmax_math.cuh"
 
 namespace stad {
 
@@ -36,24 +39,52 @@ constexpr int BKV = 128;  // keys per tile
 constexpr int K_STAGES = 4;
 constexpr int V_STAGES = 4;
 constexpr int TILE_BYTES = BQ * HD * 2;  // 16 KB: every Q / K / V tile
-constexpr int ATT_THREADS = 384;         // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1, 2: softmax slots
-constexpr int SMEM_BYTES = (2 + K_STAGES + V_STAGES) * TILE_BYTES + 512 + 1024;
+constexpr int ATT_THREADS = 512;  // warpgroups 0, 1: softmax slots; 2: epilogue; 3: TMA + 2 MMA issuers (+1 idle warp)
+constexpr int LSUM_BYTES = 2 * BQ * 4;  // row sums handed from the softmax warps to the epilogue warps
+constexpr int SMEM_BYTES = (2 + K_STAGES + V_STAGES) * TILE_BYTES + LSUM_BYTES + 512 + 1024;
+// Warp roles.  The single-thread TMA / MMA issuers sit in the HIGHEST warps: the sub-partition arbiter favours high warp
+// ids, and an issuer that has to queue behind two always-ready softmax warps paces the whole kernel (measured: ~135
+// clk per tcgen05.mma issue and ~350 clk per already-complete mbarrier wait when the issuers were warps 0-2).
+constexpr int kTmaWarp = 12;   // warps 0-3: softmax slot 0, 4-7: softmax slot 1, 8-11: epilogue
+constexpr int kMmaWarp0 = 13;  // 13: MMA issuer of slot 0, 14: of slot 1, 15: idle
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t S_COL = 0;    // + slot * 128
 constexpr uint32_t P_COL = 256;  // + slot * 64   (bf16 pairs: column k holds keys 2k, 2k+1)
 constexpr uint32_t O_COL = 384;  // + slot * 64
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-// One pair of every kPolyPeriod pairs takes its exp2 on the FMA pipe instead of the MUFU (0 = never).
-#ifndef STAD_ATT_POLY_PERIOD
-#define STAD_ATT_POLY_PERIOD 4
+
+// -DSTAD_ATT_TRACE: CTA 0 records (clock, tag) events of one softmax warp per slot and of the two MMA issuers into
+// att_trace (development builds only; read through stad_debug_read_att_trace, see tools/att_trace.py).
+#ifdef STAD_ATT_TRACE
+constexpr int kTraceCap = 2048;
+__device__ unsigned long long att_trace[4][kTraceCap];
+__device__ int att_trace_n[4];
+#define ATT_EV(role, tag)                                                                          \
+  do {                                                                                             \
+    if (blockIdx.x == 0 && tr_n < kTraceCap && (threadIdx.x & 31) == 0) {                          \
+      att_trace[role][tr_n] = (static_cast<unsigned long long>(clock64()) << 8) | (tag);           \
+      att_trace_n[role] = ++tr_n;                                                                  \
+    }                                                                                              \
+  } while (0)
+#define ATT_T(i) do { if (lane == 0 && quarter == 0) ATT_EV(slot, i); } while (0)
+#else
+#define ATT_EV(role, tag) do {} while (0)
+#define ATT_T(i) do {} while (0)
 #endif
-constexpr int kPolyPeriod = STAD_ATT_POLY_PERIOD;
 
 struct AttArgs {
   bf16* out;
   int B, H, S;
   float scale_log2;  // softmax scale * log2(e)
 };
+
+// Development switches (A/B builds): software-pipelined S load; when to wait for the P buffer.
+#ifndef STAD_ATT_PIPE
+#define STAD_ATT_PIPE 0
+#endif
+#ifndef STAD_ATT_STORE_MODE
+#define STAD_ATT_STORE_MODE 0
+#endif
 
 struct Unit {
   int b, h, q0, slots;
@@ -70,74 +101,6 @@ STAD_DEVICE Unit decode_unit(int u, int units_per_head, int H, int S) {
   return w;
 }
 
-STAD_DEVICE float max3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-// packed two-lane fp32 math (FFMA2 / FADD2)
-STAD_DEVICE void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
-}
-STAD_DEVICE void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
-STAD_DEVICE float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// 2^x for a pair, entirely on the FMA/ALU pipes: x = n + f, n = round(x), f in [-0.5, 0.5];
-// 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far below bf16 resolution of P), n added to the
-// exponent field.  x is clamped at -125 so the exponent never wraps.
-STAD_DEVICE void exp2_poly2(float& e0, float& e1, float x0, float x1) {
-  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: x + kMagic holds round(x) in its low mantissa bits
-  x0 = fmaxf(x0, -125.f);
-  x1 = fmaxf(x1, -125.f);
-  float r0, r1, n0, n1, f0, f1, p0, p1;
-  add2(r0, r1, x0, x1, kMagic, kMagic);
-  add2(n0, n1, r0, r1, -kMagic, -kMagic);
-  fma2(f0, f1, n0, n1, -1.f, -1.f, x0, x1);
-  fma2(p0, p1, f0, f1, 0.05517164245247841f, 0.05517164245247841f, 0.2426111400127411f, 0.2426111400127411f);
-  fma2(p0, p1, p0, p1, f0, f1, 0.6932609677314758f, 0.6932609677314758f);
-  fma2(p0, p1, p0, p1, f0, f1, 0.9999280571937561f, 0.9999280571937561f);
-  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
-  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
-}
-
-// exp2(s * c - m) of one 32-column chunk of a score row -> 16 packed bf16 pairs; adds the fp32 row sum into acc.
-template <bool kPoly>
-STAD_DEVICE void exp_chunk(const uint32_t (&s)[32], float c, float neg_m, float& acc0, float& acc1,
-                           uint32_t (&pk)[16]) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float x0, x1, e0, e1;
-    fma2(x0, x1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), c, c, neg_m, neg_m);
-    if (kPoly && kPolyPeriod > 0 && (i % (kPolyPeriod > 0 ? kPolyPeriod : 1)) == (kPolyPeriod - 1)) {
-      exp2_poly2(e0, e1, x0, x1);
-    } else {
-      e0 = ex2(x0);
-      e1 = ex2(x1);
-    }
-    add2(acc0, acc1, acc0, acc1, e0, e1);
-    pk[i] = pack_bf16(e0, e1);
-  }
-}
-
-STAD_DEVICE float chunk_max(const uint32_t (&s)[32]) {
-  float m = max3(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]));
-#pragma unroll
-  for (int i = 3; i < 31; i += 2) m = max3(m, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-  return fmaxf(m, __uint_as_float(s[31]));
-}
-
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -146,7 +109,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
   uint8_t* smem_q = smem;                                   // [2][16 KB]
   uint8_t* smem_k = smem_q + 2 * TILE_BYTES;                // [K_STAGES][16 KB]
   uint8_t* smem_v = smem_k + K_STAGES * TILE_BYTES;         // [V_STAGES][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + V_STAGES * TILE_BYTES);
+  float* lsum_smem = reinterpret_cast<float*>(smem_v + V_STAGES * TILE_BYTES);  // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + V_STAGES * TILE_BYTES + LSUM_BYTES);
   uint64_t* q_full = bars;                   // [2]  TMA -> MMA
   uint64_t* q_free = q_full + 2;             // [2]  MMA (last Q K^T of the unit) -> TMA
   uint64_t* k_full = q_free + 2;             // [K_STAGES]
@@ -157,9 +121,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
   uint64_t* s_free = s_full + 2;             // [2]  softmax (4 warps) -> MMA: S_j is in registers
   uint64_t* p_full = s_free + 2;             // [2]  softmax (4 warps) -> MMA: P_j stored
   uint64_t* o_full = p_full + 2;             // [2]  MMA -> softmax: P_j V_j complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* l_ready = o_full + 2;            // [2]  softmax (128 threads) -> epilogue: unit done, row sums in smem
+  uint64_t* o_free = l_ready + 2;            // [2]  epilogue (4 warps) -> MMA: O has been read, next unit may overwrite
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows every value derived from it is warp-uniform (uniform
+  // registers feed tcgen05.mma / TMA directly instead of a per-lane ELECT + R2UR.BROADCAST loop per instruction)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_q = (p.S + BQ - 1) / BQ;
   const int units_per_head = (n_q + 1) / 2;
@@ -168,7 +136,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
   const int last_valid = p.S - (n_kv - 1) * BKV;   // valid keys of the last K/V tile, 1..128
   const int last_chunks = (last_valid + 31) >> 5;  // 32-column chunks of the last tile that hold any valid key
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
@@ -177,6 +145,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
       mbar_init(&s_free[s], 4);  // one arrive per softmax warp
       mbar_init(&p_full[s], 4);
       mbar_init(&o_full[s], 1);
+      mbar_init(&l_ready[s], BQ);
+      mbar_init(&o_free[s], 4);
     }
     for (int s = 0; s < K_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
@@ -188,7 +158,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp0) {
     tmem_alloc<TMEM_COLS>(tmem_slot);
     tmem_relinquish();
   }
@@ -197,16 +167,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-    if (warp == 0 && lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
+  if (warp >= kTmaWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == kTmaWarp) {
+      // ---------------------------------------------------------------- TMA producer (whole warp; one elected lane issues)
       uint32_t kst = 0, kph = 0, vst = 0, vph = 0;
       uint32_t ucnt0 = 0, ucnt1 = 0;  // units started per slot (phase of q_full / q_free)
+      auto load_tile = [&](uint64_t* full, uint8_t* dst, int col, int row, int b) {
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full, TILE_BYTES);
+          tma_load_3d(dst, &tmap_qkv, full, col, row, b);
+        }
+        __syncwarp();
+      };
       auto load_k = [&](int j, int b, int col_k) {
         mbar_wait(&k_free[kst], kph ^ 1);
-        mbar_arrive_expect_tx(&k_full[kst], TILE_BYTES);
-        tma_load_3d(smem_k + kst * TILE_BYTES, &tmap_qkv, &k_full[kst], col_k, j * BKV, b);
+        load_tile(&k_full[kst], smem_k + kst * TILE_BYTES, col_k, j * BKV, b);
         if (++kst == K_STAGES) {
           kst = 0;
           kph ^= 1;
@@ -218,34 +194,36 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
         const int col_k = (p.H + w.h) * HD;
         const int col_v = (2 * p.H + w.h) * HD;
         mbar_wait(&q_free[0], (ucnt0 & 1) ^ 1);
-        mbar_arrive_expect_tx(&q_full[0], TILE_BYTES);
-        tma_load_3d(smem_q, &tmap_qkv, &q_full[0], col_q, w.q0, w.b);
+        load_tile(&q_full[0], smem_q, col_q, w.q0, w.b);
         ++ucnt0;
         if (w.slots > 1) {
           mbar_wait(&q_free[1], (ucnt1 & 1) ^ 1);
-          mbar_arrive_expect_tx(&q_full[1], TILE_BYTES);
-          tma_load_3d(smem_q + TILE_BYTES, &tmap_qkv, &q_full[1], col_q, w.q0 + BQ, w.b);
+          load_tile(&q_full[1], smem_q + TILE_BYTES, col_q, w.q0 + BQ, w.b);
           ++ucnt1;
         }
         load_k(0, w.b, col_k);
         for (int j = 0; j < n_kv; ++j) {
           if (j + 1 < n_kv) load_k(j + 1, w.b, col_k);
           mbar_wait(&v_free[vst], vph ^ 1);
-          mbar_arrive_expect_tx(&v_full[vst], TILE_BYTES);
-          tma_load_3d(smem_v + vst * TILE_BYTES, &tmap_qkv, &v_full[vst], col_v, j * BKV, w.b);
+          load_tile(&v_full[vst], smem_v + vst * TILE_BYTES, col_v, j * BKV, w.b);
           if (++vst == V_STAGES) {
             vst = 0;
             vph ^= 1;
           }
         }
       }
-    } else if ((warp == 1 || warp == 2) && lane == 0) {
-      // ---------------------------------------------------------------- MMA issuers: warp 1 -> slot 0, warp 2 -> slot 1
-      // One issuing thread per slot keeps the two slots independent: neither ever waits behind a barrier of the other.
-      // Both read the same K / V ring stages; a stage is released by two arrivals (one per slot; in a one-slot unit
-      // the slot-0 thread commits twice).
-      const int slot = warp - 1;
+    } else if (warp == kMmaWarp0 || warp == kMmaWarp0 + 1) {
+      // ---------------------------------------------------------------- MMA issuers: warp 13 -> slot 0, 14 -> slot 1
+      // One issuing warp per slot keeps the two slots independent: neither ever waits behind a barrier of the other.
+      // The whole warp runs the (warp-uniform) control flow and waits; one elected lane issues tcgen05.mma / commit.
+      // Both slots read the same K / V ring stages; a stage is released by two arrivals (one per slot; in a one-slot
+      // unit the slot-0 warp commits twice).
+      const int slot = warp - kMmaWarp0;
+#ifdef STAD_ATT_TRACE
+      int tr_n = 0;
+#endif
       constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);  // P from TMEM (K-major), V MN-major (d contiguous)
+      constexpr uint32_t idesc_qk_full = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major
       const uint64_t desc_q = make_smem_desc_sw128(smem_u32(smem_q + slot * TILE_BYTES), 16, 1024);
       const uint32_t tmem_s = tmem_base + S_COL + slot * BKV;
       const uint32_t tmem_p = tmem_base + P_COL + slot * (BKV / 2);
@@ -262,57 +240,139 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
           continue;
         }
         const bool solo = w.slots == 1;
-        // S = Q K^T over the first `cols` keys of the next K tile; releases the K stage
+        // S = Q K^T over the first `cols` keys of K tile number kc (its k_full wait has been done); releases the stage
         auto issue_qk = [&](int cols, bool last_of_unit) {
           const uint32_t kst = kc % K_STAGES;
-          mbar_wait(&k_full[kst], (kc / K_STAGES) & 1);
           tc_fence_after();
-          const uint32_t idesc = make_idesc_bf16(BQ, static_cast<uint32_t>(cols), 0, 0);  // Q, K both K-major
-          const uint64_t desc_k = make_smem_desc_sw128(smem_u32(smem_k + kst * TILE_BYTES), 16, 1024);
+          ATT_EV(2 + slot, 20);
+          if (elect_one()) {
+            const uint64_t desc_k = make_smem_desc_sw128(smem_u32(smem_k + kst * TILE_BYTES), 16, 1024);
+            if (cols == BKV) {
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc, k != 0);
-          umma_commit(&s_full[slot]);
-          if (last_of_unit) umma_commit(&q_free[slot]);
-          umma_commit(&k_free[kst]);
-          if (solo) umma_commit(&k_free[kst]);
+              for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc_qk_full, k != 0);
+            } else {
+              const uint32_t idesc = make_idesc_bf16(BQ, static_cast<uint32_t>(cols), 0, 0);
+#pragma unroll
+              for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc, k != 0);
+            }
+            ATT_EV(2 + slot, 21);
+            umma_commit(&s_full[slot]);
+            if (last_of_unit) umma_commit(&q_free[slot]);
+            umma_commit(&k_free[kst]);
+            if (solo) umma_commit(&k_free[kst]);
+          }
+          __syncwarp();
           ++kc;
         };
-        // O (+)= P V over the first 16 * ksteps keys.  V tile: one 128-byte row per key -> MN-major B operand;
-        // 16 keys = 2 x 1024 B per MMA.  Releases the V stage.
+        // O (+)= P V over the first 16 * ksteps keys of V tile number vc.  V tile: one 128-byte row per key -> MN-major
+        // B operand; 16 keys = 2 x 1024 B per MMA.  Releases the V stage.
         auto issue_pv = [&](bool accumulate, int ksteps) {
           const uint32_t vst = vc % V_STAGES;
-          mbar_wait(&v_full[vst], (vc / V_STAGES) & 1);
           tc_fence_after();
-          const uint64_t desc_v = make_smem_desc_sw128(smem_u32(smem_v + vst * TILE_BYTES), 0, 1024);
-          for (int k = 0; k < ksteps; ++k)
-            umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
-          umma_commit(&o_full[slot]);
-          umma_commit(&v_free[vst]);
-          if (solo) umma_commit(&v_free[vst]);
+          ATT_EV(2 + slot, 22);
+          if (elect_one()) {
+            const uint64_t desc_v = make_smem_desc_sw128(smem_u32(smem_v + vst * TILE_BYTES), 0, 1024);
+            if (ksteps == BKV / 16) {
+#pragma unroll
+              for (int k = 0; k < BKV / 16; ++k)
+                umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+            } else {
+              for (int k = 0; k < ksteps; ++k)
+                umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+            }
+            ATT_EV(2 + slot, 23);
+            umma_commit(&o_full[slot]);
+            umma_commit(&v_free[vst]);
+            if (solo) umma_commit(&v_free[vst]);
+          }
+          __syncwarp();
           ++vc;
         };
+        auto wait_k = [&]() { mbar_wait(&k_full[kc % K_STAGES], (kc / K_STAGES) & 1); };
+        auto wait_v = [&]() { mbar_wait(&v_full[vc % V_STAGES], (vc / V_STAGES) & 1); };
 
         mbar_wait(&q_full[slot], ucnt & 1);
+        wait_k();
         if (g > 0) mbar_wait(&s_free[slot], (g - 1) & 1);  // previous S of the slot has been pulled out of TMEM
         issue_qk(n_kv == 1 ? last_chunks * 32 : BKV, n_kv == 1);
         for (int j = 0; j < n_kv; ++j) {
           const bool has_next = j + 1 < n_kv;
           const bool next_last = j + 2 == n_kv;
+          // the operand tiles arrive long before the softmax signals: wait for them first, so that only the MMA issue
+          // itself follows the s_free / p_full arrival
           if (has_next) {
+            wait_k();
+            ATT_EV(2 + slot, 10);
             mbar_wait(&s_free[slot], (g + j) & 1);
+            ATT_EV(2 + slot, 11);
             issue_qk(next_last ? last_chunks * 32 : BKV, next_last);
+            ATT_EV(2 + slot, 12);
           }
+          wait_v();
+          if (j == 0 && ucnt > 0) mbar_wait(&o_free[slot], (ucnt - 1) & 1);  // epilogue has read the previous unit's O
           mbar_wait(&p_full[slot], (g + j) & 1);
+          ATT_EV(2 + slot, 13);
           issue_pv(j != 0, has_next ? BKV / 16 : last_chunks * 2);
+          ATT_EV(2 + slot, 14);
         }
         g += n_kv;
         ++ucnt;
       }
     }
+  } else if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    // ------------------------------------------------------------------ epilogue warps: O / l -> bf16 -> global
+    // Takes the end-of-unit work off the softmax warps: they hand over the row sums and move on to the next unit.
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    uint32_t gs[2] = {0, 0};    // iterations completed per slot
+    uint32_t ucs[2] = {0, 0};   // units completed per slot
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const Unit w = decode_unit(u, units_per_head, p.H, p.S);
+#pragma unroll
+      for (int slot = 0; slot < 2; ++slot) {
+        if (slot >= w.slots) continue;
+        gs[slot] += n_kv;
+        mbar_wait(&l_ready[slot], ucs[slot] & 1);          // every softmax thread of the slot finished the unit
+        mbar_wait(&o_full[slot], (gs[slot] - 1) & 1);      // last P V of the unit
+        tc_fence_after();
+        ++ucs[slot];
+        const int row = w.q0 + slot * BQ + r;
+        const bool warp_valid = w.q0 + slot * BQ + quarter * 32 < p.S;
+        const float inv = 1.0f / lsum_smem[slot * BQ + r];
+        const uint32_t o_addr = lane_addr + O_COL + slot * HD;
+        uint4* op = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(w.b) * p.S + row) * (p.H * HD) + w.h * HD);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t ov[32];
+          if (warp_valid) {
+            tmem_ld32(o_addr + q * 32, ov);
+            tmem_ld_wait32(ov);
+          }
+          if (q == 1) {  // O is in registers: the next unit's first P V may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free[slot]);
+          }
+          if (warp_valid && row < p.S) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 o;
+              o.x = pack_bf16(__uint_as_float(ov[i + 0]) * inv, __uint_as_float(ov[i + 1]) * inv);
+              o.y = pack_bf16(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+              o.z = pack_bf16(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+              o.w = pack_bf16(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+              op[q * 4 + (i >> 3)] = o;
+            }
+          }
+        }
+      }
+    }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ------------------------------------------------------------------ softmax warps (one query row per thread)
-    const int slot = (warp - 4) >> 2;
+    const int slot = warp >> 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -320,7 +380,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
     const uint32_t p_addr = lane_addr + P_COL + slot * (BKV / 2);
     const uint32_t o_addr = lane_addr + O_COL + slot * HD;
     const float c = p.scale_log2;
+    const bool last_full = last_valid == BKV;
     uint32_t g = 0;  // iterations completed by this slot
+#ifdef STAD_ATT_TRACE
+    int tr_n = 0;
+#endif
+
+    // Lazy rescale of this thread's O row (rare: only when the running max grew by more than 2^8).
+    auto rescale_o = [&](float alpha) {
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        uint32_t ov[32];
+        tmem_ld32(o_addr + q * 32, ov);
+        tmem_ld_wait32(ov);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+        tmem_st32(o_addr + q * 32, ov);
+      }
+    };
 
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const Unit w = decode_unit(u, units_per_head, p.H, p.S);
@@ -329,14 +406,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
       const bool warp_valid = row0 + quarter * 32 < p.S;  // warp-uniform: any valid query row in this warp
       float m_ref = 0.f;  // reference max (log2 domain, already scaled)
       float l_sum = 0.f;
+      uint32_t sv[4][32];
+      bool have_s = false;  // S_j was pulled into sv by the previous iteration (software pipelining)
 
       for (int j = 0; j < n_kv; ++j, ++g) {
-        mbar_wait(&s_full[slot], g & 1);
-        tc_fence_after();
+        ATT_T(7);
         if (!warp_valid) {
           // rows beyond S: nothing to compute (their P / O rows are never stored); keep the pipeline moving.
           // The p_full arrival must not overtake phase j-1 of that barrier (the computing warps may still be
           // working on P_{j-1}); P V_{j-1} done implies p_full phase j-1 has completed.
+          mbar_wait(&s_full[slot], g & 1);
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(&s_free[slot]);
@@ -345,20 +424,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
           }
           continue;
         }
-        const bool full_tile = (j + 1 < n_kv) || last_valid == BKV;
+        const bool full_tile = (j + 1 < n_kv) || last_full;
         if (full_tile) {
-          uint32_t sv[4][32];
-          tmem_ld32(s_addr + 0, sv[0]);
-          tmem_ld32(s_addr + 32, sv[1]);
-          tmem_ld32(s_addr + 64, sv[2]);
-          tmem_ld32(s_addr + 96, sv[3]);
-          tmem_ld_wait32(sv[0]);
-          tmem_ld_wait32(sv[1]);
-          tmem_ld_wait32(sv[2]);
-          tmem_ld_wait32(sv[3]);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[slot]);  // S_j is in registers: Q K_{j+1}^T may overwrite it
+          if (!have_s) {
+            mbar_wait(&s_full[slot], g & 1);
+            tc_fence_after();
+            ATT_T(0);
+            tmem_ld32(s_addr + 0, sv[0]);
+            tmem_ld32(s_addr + 32, sv[1]);
+            tmem_ld32(s_addr + 64, sv[2]);
+            tmem_ld32(s_addr + 96, sv[3]);
+            tmem_ld_wait32(sv[0]);
+            tmem_ld_wait32(sv[1]);
+            tmem_ld_wait32(sv[2]);
+            tmem_ld_wait32(sv[3]);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[slot]);  // S_j is in registers: Q K_{j+1}^T may overwrite it
+          }
+          ATT_T(1);
 
           const float mx = c * max3(fmaxf(chunk_max(sv[0]), chunk_max(sv[1])), chunk_max(sv[2]), chunk_max(sv[3]));
           bool pv_done = (j == 0);  // P V of the previous iteration finished (P buffer reusable, O stable)
@@ -376,33 +460,80 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
                 m_ref = mx;
                 l_sum *= alpha;
               }
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                uint32_t ov[32];
-                tmem_ld32(o_addr + q * 32, ov);
-                tmem_ld_wait32(ov);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-                tmem_st32(o_addr + q * 32, ov);
-              }
+              rescale_o(alpha);
             }
           }
+          ATT_T(2);
           const float neg_m = -m_ref;
           float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t pk[16];
-            if (q & 1) exp_chunk<true>(sv[q], c, neg_m, b0, b1, pk);
-            else exp_chunk<true>(sv[q], c, neg_m, a0, a1, pk);
-            if (q == 0 && !pv_done) {
+          const bool next_full = STAD_ATT_PIPE && ((j + 2 < n_kv) || (j + 1 < n_kv && last_full));
+          // Each chunk's P is stored as soon as it is packed (keeps the chunks' instruction streams apart: FFMA2, MUFU
+          // and F2FP of neighbouring chunks overlap, but the scheduler cannot lump all MUFUs of the tile together).
+          {
+            uint32_t pk0[16], pk1[16];
+            exp_chunk<true>(sv[0], c, neg_m, a0, a1, pk0);
+#if STAD_ATT_STORE_MODE == 0
+            ATT_T(8);
+            if (!pv_done) {
               mbar_wait(&o_full[slot], (g - 1) & 1);  // P V_{j-1} has consumed the P buffer
               tc_fence_after();
             }
-            tmem_st16(p_addr + q * 16, pk);
+            ATT_T(9);
+            tmem_st16(p_addr, pk0);
+            exp_chunk<true>(sv[1], c, neg_m, b0, b1, pk1);
+            tmem_st16(p_addr + 16, pk1);
+#else
+            const bool o_ok = pv_done || mbar_try_wait(&o_full[slot], (g - 1) & 1);
+            exp_chunk<true>(sv[1], c, neg_m, b0, b1, pk1);
+            if (!o_ok) mbar_wait(&o_full[slot], (g - 1) & 1);
+            tc_fence_after();
+            tmem_st16(p_addr, pk0);
+            tmem_st16(p_addr + 16, pk1);
+#endif
+          }
+          {
+            uint32_t pk2[16];
+            exp_chunk<true>(sv[2], c, neg_m, a0, a1, pk2);
+            tmem_st16(p_addr + 32, pk2);
+          }
+          bool s_ok = false;
+          if (next_full) s_ok = mbar_try_wait(&s_full[slot], (g + 1) & 1);
+          {
+            uint32_t pk3[16];
+            exp_chunk<true>(sv[3], c, neg_m, b0, b1, pk3);
+            tmem_st16(p_addr + 48, pk3);
           }
           l_sum += (a0 + a1) + (b0 + b1);
+          ATT_T(3);
+          if (next_full) {
+            // pull S_{j+1} while the P stores drain: the score registers are free again
+            if (!s_ok) mbar_wait(&s_full[slot], (g + 1) & 1);
+            tc_fence_after();
+            tmem_ld32(s_addr + 0, sv[0]);
+            tmem_ld32(s_addr + 32, sv[1]);
+            tmem_ld32(s_addr + 64, sv[2]);
+            tmem_ld32(s_addr + 96, sv[3]);
+          }
+          ATT_T(4);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[slot]);
+          if (next_full) {
+            tmem_ld_wait32(sv[0]);
+            tmem_ld_wait32(sv[1]);
+            tmem_ld_wait32(sv[2]);
+            tmem_ld_wait32(sv[3]);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[slot]);
+          }
+          have_s = next_full;
+          ATT_T(5);
         } else {
           // ---- last K/V tile with fewer than 128 valid keys: chunk loop, S read twice (max pass, exp pass)
+          mbar_wait(&s_full[slot], g & 1);
+          tc_fence_after();
           float rmax = -INFINITY;
 #pragma unroll 1
           for (int q = 0; q < last_chunks; ++q) {
@@ -418,34 +549,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
             rmax = fmaxf(rmax, chunk_max(t));
           }
           const float mx = c * rmax;
-          bool pv_done = (j == 0);
           if (j == 0) {
             m_ref = mx;
           } else {
+            mbar_wait(&o_full[slot], (g - 1) & 1);
+            tc_fence_after();
             const bool grow = mx > m_ref + kRescaleThreshold;
             if (__any_sync(0xffffffffu, grow)) {
-              mbar_wait(&o_full[slot], (g - 1) & 1);
-              tc_fence_after();
-              pv_done = true;
               const float alpha = grow ? ex2(m_ref - mx) : 1.0f;
               if (grow) {
                 m_ref = mx;
                 l_sum *= alpha;
               }
-#pragma unroll 1
-              for (int q = 0; q < 2; ++q) {
-                uint32_t ov[32];
-                tmem_ld32(o_addr + q * 32, ov);
-                tmem_ld_wait32(ov);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-                tmem_st32(o_addr + q * 32, ov);
-              }
+              rescale_o(alpha);
             }
-          }
-          if (!pv_done) {
-            mbar_wait(&o_full[slot], (g - 1) & 1);
-            tc_fence_after();
           }
           const float neg_m = -m_ref;
           float a0 = 0.f, a1 = 0.f;
@@ -468,44 +585,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_free[slot]);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[slot]);
-      }
-
-      // ---- finalise: O / l  -> bf16 -> out[b, row0 + r, h*64 .. h*64+63]
-      if (warp_valid) {
-        mbar_wait(&o_full[slot], (g - 1) & 1);
-        tc_fence_after();
-        const int row = row0 + r;
-        const float inv = 1.0f / l_sum;
-        uint4* op = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(w.b) * p.S + row) * (p.H * HD) + w.h * HD);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          uint32_t ov[32];
-          tmem_ld32(o_addr + q * 32, ov);
-          tmem_ld_wait32(ov);
-          if (row < p.S) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 o;
-              o.x = pack_bf16(__uint_as_float(ov[i + 0]) * inv, __uint_as_float(ov[i + 1]) * inv);
-              o.y = pack_bf16(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
-              o.z = pack_bf16(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
-              o.w = pack_bf16(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
-              op[q * 4 + (i >> 3)] = o;
-            }
-          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[slot]);
+          have_s = false;
         }
       }
+      // ---- hand the row sum to the epilogue warps and go on with the next unit
+      lsum_smem[slot * BQ + r] = l_sum;
+      mbar_arrive(&l_ready[slot]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp0) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -513,6 +608,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
 }
 
 }  // namespace
+
+#ifdef STAD_ATT_TRACE
+extern "C" __attribute__((visibility("default"))) int stad_debug_read_att_trace(unsigned long long* out, int* counts) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, att_trace, sizeof(unsigned long long) * 4 * kTraceCap);
+  cudaMemcpyFromSymbol(counts, att_trace_n, sizeof(int) * 4);
+  int zero[4] = {0, 0, 0, 0};
+  cudaMemcpyToSymbol(att_trace_n, zero, sizeof(zero));
+  return kTraceCap;
+}
+#endif
 
 int attention_init() {
   STAD_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

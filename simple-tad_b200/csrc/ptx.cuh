@@ -65,11 +65,7 @@ STAD_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 STAD_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > STAD_WAIT_SPIN_LIMIT) {
-      printf("stad: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x);
-      __trap();
-    }
+    if (++spins > STAD_WAIT_SPIN_LIMIT) __trap();  // surfaces as cudaErrorLaunchFailure instead of a hung device
   }
 }
 
