@@ -100,7 +100,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* buf_ready_bar = tmem_empty_bar + 2;  // [warpgroup][buffer]: staging buffer free (+ residual landed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_ready_bar + 4);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows every value derived from it is warp-uniform, and the
+  // single-lane TMA / tcgen05.mma issue below takes its operands straight from uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int num_kb = p.K / BK;
@@ -132,24 +134,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles;
-        const int n_tile = tile % p.n_tiles;
-        int a_bytes = C::A_BYTES;
-        int pe_b = 0, pe_tp = 0, pe_h0 = 0;
-        if constexpr (kPatch) {
-          const PatchGeom& g = p.pg;
-          const int hh = m_tile % g.h_tiles;
-          pe_tp = (m_tile / g.h_tiles) % g.Tp;
-          pe_b = m_tile / (g.h_tiles * g.Tp);
-          pe_h0 = hh * g.hp_tile;
-          a_bytes = g.Wp * g.hp_tile * BK * 2;  // 4 full boxes, out-of-range h' rows arrive as zeros
-        }
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // The whole warp runs the (warp-uniform) loop and the waits; one elected lane issues the copies.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile % p.n_tiles;
+      int a_bytes = C::A_BYTES;
+      int pe_b = 0, pe_tp = 0, pe_h0 = 0;
+      if constexpr (kPatch) {
+        const PatchGeom& g = p.pg;
+        const int hh = m_tile % g.h_tiles;
+        pe_tp = (m_tile / g.h_tiles) % g.Tp;
+        pe_b = m_tile / (g.h_tiles * g.Tp);
+        pe_h0 = hh * g.hp_tile;
+        a_bytes = g.Wp * g.hp_tile * BK * 2;  // 4 full boxes, out-of-range h' rows arrive as zeros
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], a_bytes + C::B_BYTES);
@@ -169,29 +172,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_tile * BM);
           }
           tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_tile * BN);
-          if (++stage == C::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+    // Whole warp in the loop (waits, bookkeeping); one elected lane issues tcgen05.mma / tcgen05.commit.
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
           const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
@@ -210,12 +215,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
           }
           umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
-          if (++stage == C::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else {
@@ -225,7 +231,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int wg = ew >> 2;        // warpgroup = which half of the BN columns
     constexpr int COLS = BN / 2;
     constexpr int CHUNKS = COLS / kSubCols;
-    const bool leader = (ew & 3) == 0 && lane == 0;  // issues the TMA traffic of this warpgroup
+    const bool lead_warp = (ew & 3) == 0;            // its elected lane issues the TMA traffic of this warpgroup
     const int r = quarter * 32 + lane;               // accumulator row (TMEM lane) of this thread
     uint8_t* stage_buf = staging + wg * 2 * kSubTileBytes;
     uint64_t* ready = buf_ready_bar + wg * 2;
@@ -259,7 +265,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     };
 
     int ci = 0;
-    if (leader) prepare_buffer(0);
+    if (lead_warp) {
+      if (elect_one()) prepare_buffer(0);
+      __syncwarp();
+    }
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int m_tile = tile / p.n_tiles;
@@ -372,14 +381,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         fence_proxy_async_smem();         // generic-proxy writes -> visible to the TMA (async proxy)
         named_bar_sync(1 + wg, 128);      // whole sub-tile staged
-        if (leader) {
-          tma_store_2d(&tmap_out, buf, n0, tr.row0);  // rows beyond M (or beyond the box) are clipped by the TMA
-          tma_store_commit();
-          prepare_buffer(ci + 1);
+        if (lead_warp) {
+          if (elect_one()) {  // deterministic: always the same lane, which owns the bulk async-groups
+            tma_store_2d(&tmap_out, buf, n0, tr.row0);  // rows beyond M (or beyond the box) are clipped by the TMA
+            tma_store_commit();
+            prepare_buffer(ci + 1);
+          }
+          __syncwarp();
         }
       }
     }
-    if (leader) tma_store_wait<0>();  // all output tiles of this CTA are in global memory
+    if (lead_warp) {
+      if (elect_one()) tma_store_wait<0>();  // all output tiles of this CTA are in global memory
+      __syncwarp();
+    }
   }
 
   tc_fence_before();
