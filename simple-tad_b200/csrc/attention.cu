@@ -61,12 +61,12 @@ __device__ unsigned long long att_trace[4][kTraceCap];
 __device__ int att_trace_n[4];
 #define ATT_EV(role, tag)                                                                          \
   do {                                                                                             \
-    if (blockIdx.x == 0 && tr_n < kTraceCap && (threadIdx.x & 31) == 0) {                          \
+    if ((STAD_ATT_TRACE >= 2 || (role) < 2) && blockIdx.x == 0 && tr_n < kTraceCap && (threadIdx.x & 31) == 0) {                          \
       att_trace[role][tr_n] = (static_cast<unsigned long long>(clock64()) << 8) | (tag);           \
       att_trace_n[role] = ++tr_n;                                                                  \
     }                                                                                              \
   } while (0)
-#define ATT_T(i) do { if (lane == 0 && quarter == 0) ATT_EV(slot, i); } while (0)
+#define ATT_T(i) do { if ((STAD_ATT_TRACE >= 2 || (i) == 7 || (i) == 2) && lane == 0 && quarter == 0) ATT_EV(slot, i); } while (0)
 #else
 #define ATT_EV(role, tag) do {} while (0)
 #define ATT_T(i) do {} while (0)
@@ -81,6 +81,15 @@ struct AttArgs {
 // Development switches (A/B builds): software-pipelined S load; when to wait for the P buffer.
 #ifndef STAD_ATT_PIPE
 #define STAD_ATT_PIPE 0
+#endif
+#ifndef STAD_ATT_STAGGER
+#define STAD_ATT_STAGGER 0
+#endif
+#ifndef STAD_ATT_PROBE
+#define STAD_ATT_PROBE 1
+#endif
+#ifndef STAD_ATT_SPLIT_LD
+#define STAD_ATT_SPLIT_LD 1
 #endif
 #ifndef STAD_ATT_STORE_MODE
 #define STAD_ATT_STORE_MODE 0
@@ -408,9 +417,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
       float l_sum = 0.f;
       uint32_t sv[4][32];
       bool have_s = false;  // S_j was pulled into sv by the previous iteration (software pipelining)
+      bool s_probe = false; // s_full of the coming iteration was already seen complete
 
       for (int j = 0; j < n_kv; ++j, ++g) {
         ATT_T(7);
+#if STAD_ATT_STAGGER
+        // One-time phase offset between the two slots: without it both softmax warpgroups run in lockstep (same
+        // phase of the iteration at the same time), i.e. they fight for the MUFU together and idle together.
+        if (g == 0) {
+          if (slot == 1) named_bar_sync(1, 2 * BQ);
+          else if (!warp_valid) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+        }
+#endif
         if (!warp_valid) {
           // rows beyond S: nothing to compute (their P / O rows are never stored); keep the pipeline moving.
           // The p_full arrival must not overtake phase j-1 of that barrier (the computing warps may still be
@@ -426,10 +444,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
         }
         const bool full_tile = (j + 1 < n_kv) || last_full;
         if (full_tile) {
+          float mx;
           if (!have_s) {
-            mbar_wait(&s_full[slot], g & 1);
+            if (!s_probe) mbar_wait(&s_full[slot], g & 1);  // usually already seen complete by last iteration's probe
             tc_fence_after();
             ATT_T(0);
+#if STAD_ATT_SPLIT_LD
+            // two loads, wait, two more loads in flight while the first half's row max is computed
+            tmem_ld32(s_addr + 0, sv[0]);
+            tmem_ld32(s_addr + 32, sv[1]);
+            tmem_ld_wait32(sv[0]);
+            tmem_ld_wait32(sv[1]);
+            tmem_ld32(s_addr + 64, sv[2]);
+            tmem_ld32(s_addr + 96, sv[3]);
+            const float m01 = fmaxf(chunk_max(sv[0]), chunk_max(sv[1]));
+            tmem_ld_wait32(sv[2]);
+            tmem_ld_wait32(sv[3]);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[slot]);  // S_j is in registers: Q K_{j+1}^T may overwrite it
+            ATT_T(1);
+            mx = c * max3(m01, chunk_max(sv[2]), chunk_max(sv[3]));
+#else
             tmem_ld32(s_addr + 0, sv[0]);
             tmem_ld32(s_addr + 32, sv[1]);
             tmem_ld32(s_addr + 64, sv[2]);
@@ -441,10 +477,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_free[slot]);  // S_j is in registers: Q K_{j+1}^T may overwrite it
+            ATT_T(1);
+            mx = c * max3(fmaxf(chunk_max(sv[0]), chunk_max(sv[1])), chunk_max(sv[2]), chunk_max(sv[3]));
+#endif
+          } else {
+            ATT_T(1);
+            mx = c * max3(fmaxf(chunk_max(sv[0]), chunk_max(sv[1])), chunk_max(sv[2]), chunk_max(sv[3]));
           }
-          ATT_T(1);
-
-          const float mx = c * max3(fmaxf(chunk_max(sv[0]), chunk_max(sv[1])), chunk_max(sv[2]), chunk_max(sv[3]));
+          s_probe = false;
           bool pv_done = (j == 0);  // P V of the previous iteration finished (P buffer reusable, O stable)
           if (j == 0) {
             m_ref = mx;
@@ -464,6 +504,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
             }
           }
           ATT_T(2);
+          // probe the barrier the first P store needs while chunk 0 is computed (the probe's latency is hidden)
+          const bool o_probe = !pv_done && STAD_ATT_PROBE && mbar_try_wait(&o_full[slot], (g - 1) & 1);
           const float neg_m = -m_ref;
           float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
           const bool next_full = STAD_ATT_PIPE && ((j + 2 < n_kv) || (j + 1 < n_kv && last_full));
@@ -474,14 +516,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
             exp_chunk<true>(sv[0], c, neg_m, a0, a1, pk0);
 #if STAD_ATT_STORE_MODE == 0
             ATT_T(8);
-            if (!pv_done) {
-              mbar_wait(&o_full[slot], (g - 1) & 1);  // P V_{j-1} has consumed the P buffer
-              tc_fence_after();
-            }
+            if (!pv_done && !o_probe) mbar_wait(&o_full[slot], (g - 1) & 1);  // P V_{j-1} has consumed the P buffer
+            tc_fence_after();
             ATT_T(9);
             tmem_st16(p_addr, pk0);
             exp_chunk<true>(sv[1], c, neg_m, b0, b1, pk1);
             tmem_st16(p_addr + 16, pk1);
+#if STAD_ATT_STAGGER
+            if (g == 0 && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+#endif
 #else
             const bool o_ok = pv_done || mbar_try_wait(&o_full[slot], (g - 1) & 1);
             exp_chunk<true>(sv[1], c, neg_m, b0, b1, pk1);
@@ -515,6 +558,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
             tmem_ld32(s_addr + 96, sv[3]);
           }
           ATT_T(4);
+          if (STAD_ATT_PROBE && !next_full && j + 1 < n_kv) s_probe = mbar_try_wait(&s_full[slot], (g + 1) & 1);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
@@ -582,6 +626,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
             tmem_st16(p_addr + q * 16, pk);
           }
           l_sum += a0 + a1;
+#if STAD_ATT_STAGGER
+          if (g == 0 && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+#endif
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_free[slot]);
