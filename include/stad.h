@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define STAD_ABI_VERSION 1
+#define STAD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define STAD_API __attribute__((visibility("default")))
@@ -126,11 +126,11 @@ STAD_API const char* stad_last_error(void);
  * Not CUDA-graph capturable; leave disabled (the default) outside benchmarks. */
 enum {
   STAD_K_CAST = 0, STAD_K_GATHER = 1, STAD_K_GEMM = 2, STAD_K_ATTENTION = 3, STAD_K_ROW_STATS = 4,
-  STAD_K_LAYERNORM = 5, STAD_K_POOL = 6
+  STAD_K_LAYERNORM = 5, STAD_K_POOL = 6 /* ROW_STATS with epi = 1: stad_stats_finalize */
 };
 typedef struct stad_profile_record {
   int32_t kind;    /* STAD_K_*                                                        */
-  int32_t epi;     /* GEMM: 1 LN-fold | 2 GELU | 4 residual | 8 pos table | 16 patch-embed (5-D TMA) A operand */
+  int32_t epi;     /* GEMM: 1 LN-fold | 2 GELU | 4 residual | 8 pos table | 16 emits LN partial sums | 32 patch-embed A operand */
   int32_t m, n, k; /* GEMM: M, N, K; attention: B, H, S; row kernels: rows, cols, 0  */
   float ms;        /* device time between the two events                             */
 } stad_profile_record;
@@ -173,6 +173,20 @@ STAD_API int stad_ln_gemm(const void* x, const float* stats, const void* w, cons
  *   fc2 + residual (mf:52, mf:162).  residual may be NULL (plain Linear) and may alias out. */
 STAD_API int stad_gemm_bias_residual(const void* a, const void* w, const float* bias, const void* residual, void* out, int M,
                             int N, int K, stad_stream_t stream);
+
+/* ---- LayerNorm statistics without a pass over x ------------------------------------------------------------------
+ * The GEMM that writes the residual stream x also emits, per row, `parts` partial (sum, sum of squares) pairs of the
+ * bf16 values it stored (one pair per column tile and epilogue warpgroup, laid out [parts, M]); stad_stats_finalize
+ * adds them in index order (deterministic, no atomics) into the (mean, rstd) that stad_ln_gemm takes.  Replaces
+ * stad_row_stats on the whole-model path.   nn.LayerNorm statistics of norm1 / norm2, mf:143/149; x = x + ..., mf:161-162. */
+/* Number of partial pairs per row that stad_gemm_bias_residual_stats writes for an [M, N] output. */
+STAD_API int stad_stat_parts(int M, int N);
+/* stad_gemm_bias_residual + statistics: stat_parts is float[parts, M, 2], parts = stad_stat_parts(M, N). */
+STAD_API int stad_gemm_bias_residual_stats(const void* a, const void* w, const float* bias, const void* residual, void* out,
+                                  float* stat_parts, int M, int N, int K, stad_stream_t stream);
+/* stat_parts float[parts, M, 2] -> stats float[M, 2] = (mean, rstd) over D columns, rstd = 1 / sqrt(var + eps). */
+STAD_API int stad_stats_finalize(const float* stat_parts, int parts, float* stats, int M, int D, float eps,
+                        stad_stream_t stream);
 
 /* Joint space-time softmax(q k^T * scale) v over packed qkv[B, S, 3, H, 64] bf16 -> out[B, S, H*64] bf16.
  *   Same tensor contract as FlashAttention.forward (fac:26-51, qkv "(B, S, 3, H, D)") and the math of

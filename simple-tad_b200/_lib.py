@@ -16,7 +16,8 @@ STAD_IN_CLIPS, STAD_IN_FRAMES = 0, 1
 EXPORTS = (
     "stad_abi_version", "stad_init", "stad_last_error", "stad_cast_f32_bf16", "stad_row_stats", "stad_layernorm",
     "stad_pool_norm_head", "stad_patch_embed", "stad_ln_gemm", "stad_gemm_bias_residual", "stad_attention",
-    "stad_workspace_bytes", "stad_vit_forward", "stad_profile_enable", "stad_profile_read",
+    "stad_workspace_bytes", "stad_vit_forward", "stad_profile_enable", "stad_profile_read", "stad_stat_parts",
+    "stad_gemm_bias_residual_stats", "stad_stats_finalize",
 )
 
 
@@ -79,6 +80,9 @@ def load():
         "stad_ln_gemm": (C.c_int, [vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp]),
         "stad_gemm_bias_residual": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "stad_attention": (C.c_int, [vp, vp, i32, i32, i32, f32, vp]),
+        "stad_stat_parts": (C.c_int, [i32, i32]),
+        "stad_gemm_bias_residual_stats": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+        "stad_stats_finalize": (C.c_int, [vp, i32, vp, i32, i32, f32, vp]),
         "stad_workspace_bytes": (sz, [C.POINTER(StadDims), i32, i32]),
         "stad_profile_enable": (C.c_int, [i32]),
         "stad_profile_read": (C.c_int, [C.POINTER(StadProfileRecord), i32]),
@@ -221,6 +225,27 @@ def gemm_bias_residual(a, w, bias=None, residual=None, out=None):
     check(load().stad_gemm_bias_residual(ptr(a), ptr(w), ptr(bias), ptr(residual), ptr(out), M, N, K, stream_ptr()),
           "stad_gemm_bias_residual")
     return out
+
+
+def gemm_bias_residual_stats(a, w, bias, residual, eps, out=None):
+    """out = a w^T + bias + residual, plus the LayerNorm statistics (mean, rstd) [M, 2] of the rows of out, obtained
+    from the partial sums the GEMM epilogue emits (no pass over out): returns (out, stats)."""
+    init(a.device)
+    _req(a, torch.bfloat16, "a")
+    _req(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"gemm: a is [{M},{K}] but w is {tuple(w.shape)}")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    P = check(load().stad_stat_parts(M, N), "stad_stat_parts")
+    parts = torch.empty(P, M, 2, dtype=torch.float32, device=a.device)
+    check(load().stad_gemm_bias_residual_stats(ptr(a), ptr(w), ptr(bias), ptr(residual), ptr(out), ptr(parts), M, N, K,
+                                               stream_ptr()), "stad_gemm_bias_residual_stats")
+    stats = torch.empty(M, 2, dtype=torch.float32, device=a.device)
+    check(load().stad_stats_finalize(ptr(parts), P, ptr(stats), M, N, float(eps), stream_ptr()), "stad_stats_finalize")
+    return out, stats
 
 
 def attention(qkv, scale=None, out=None):

@@ -66,7 +66,8 @@ size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct Workspace {
   bf16* x;       // [M, D]   residual stream
-  float2* stats; // [M]
+  float2* stats; // [M]            LayerNorm (mean, rstd) of x
+  float2* parts; // [2 D / 64, M]  partial (sum, sumsq) written by the GEMM that produced x
   bf16* qkv;     // [M, 3D]
   bf16* attn;    // [M, D]   (directly after qkv)
   bf16* hidden;  // [M, 4D]  aliases qkv+attn: qkv/attn are dead once proj has run
@@ -89,6 +90,7 @@ Workspace carve(const stad_dims* d, int B, int n_tok, void* base) {
   uint8_t* p = static_cast<uint8_t*>(base);
   const size_t o_x = take(M * D * 2);
   const size_t o_stats = take(M * sizeof(float2));
+  const size_t o_parts = take(M * (2 * D / 64) * sizeof(float2));
   const size_t hid = static_cast<size_t>(d->hidden) > 4 * D ? d->hidden : 4 * D;
   const size_t o_big = take(M * hid * 2);
   const size_t o_pool = take(static_cast<size_t>(B) * 16 * D * sizeof(float));
@@ -96,6 +98,7 @@ Workspace carve(const stad_dims* d, int B, int n_tok, void* base) {
   const size_t o_gather = take(n_tok == n_full ? 0 : M * K * 2);  // im2col scratch only on the visible-token path
   w.x = reinterpret_cast<bf16*>(p + o_x);
   w.stats = reinterpret_cast<float2*>(p + o_stats);
+  w.parts = reinterpret_cast<float2*>(p + o_parts);
   w.qkv = reinterpret_cast<bf16*>(p + o_big);
   w.attn = w.qkv + M * 3 * D;
   w.hidden = w.qkv;
@@ -106,7 +109,8 @@ Workspace carve(const stad_dims* d, int B, int n_tok, void* base) {
 }
 
 int patch_embed_impl(const stad_input* in, const void* w, const float* pos_bias, const int32_t* tok_idx, void* out,
-                     void* gather, const stad_dims* d, int B, int n_tok, cudaStream_t stream, int* launches) {
+                     void* gather, const stad_dims* d, int B, int n_tok, cudaStream_t stream, int* launches,
+                     float2* stats_out = nullptr, int* stat_parts = nullptr) {
   PatchGeom pg;
   int rc = make_geom(d, in, B, &pg);
   if (rc) return rc;
@@ -126,6 +130,11 @@ int patch_embed_impl(const stad_input* in, const void* w, const float* pos_bias,
     g.M = B * N_full;
     g.pos_rows = N_full;
     g.patch = &pg;
+    if (stats_out) {
+      g.epi |= EPI_STATS;
+      g.stats_out = stats_out;
+      *stat_parts = gemm_stat_parts(g.M, g.N, true, &pg);
+    }
     if ((rc = launch_gemm(g, stream))) return rc;
     *launches += 1;
   } else {
@@ -138,6 +147,11 @@ int patch_embed_impl(const stad_input* in, const void* w, const float* pos_bias,
     g.M = B * n_tok;
     g.tok_idx = tok_idx;
     g.pos_rows = N_full;
+    if (stats_out) {
+      g.epi |= EPI_STATS;
+      g.stats_out = stats_out;
+      *stat_parts = gemm_stat_parts(g.M, g.N, false, nullptr);
+    }
     if ((rc = launch_gemm(g, stream))) return rc;
     *launches += 2;
   }
@@ -239,6 +253,34 @@ int stad_gemm_bias_residual(const void* a, const void* w, const float* bias, con
   return launch_gemm(g, as_stream(stream));
 }
 
+int stad_stat_parts(int M, int N) {
+  if (M <= 0 || N <= 0 || N % 64 != 0) return fail(STAD_E_SHAPE, "stat_parts: M=%d N=%d", M, N);
+  return gemm_stat_parts(M, N, false, nullptr);
+}
+
+int stad_gemm_bias_residual_stats(const void* a, const void* w, const float* bias, const void* residual, void* out,
+                                  float* stat_parts, int M, int N, int K, stad_stream_t stream) {
+  STAD_CHECK_ARG(stat_parts != nullptr, "gemm_bias_residual_stats: stat_parts is NULL");
+  GemmArgs g;
+  g.a = static_cast<const bf16*>(a);
+  g.w = static_cast<const bf16*>(w);
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.epi = (residual ? EPI_RESID : EPI_POS) | EPI_STATS;
+  STAD_CHECK_ARG(residual != nullptr, "gemm_bias_residual_stats: the statistics epilogue exists for the residual GEMMs");
+  g.bias = bias;
+  g.residual = static_cast<const bf16*>(residual);
+  g.out = static_cast<bf16*>(out);
+  g.stats_out = reinterpret_cast<float2*>(stat_parts);
+  return launch_gemm(g, as_stream(stream));
+}
+
+int stad_stats_finalize(const float* stat_parts, int parts, float* stats, int M, int D, float eps, stad_stream_t stream) {
+  return launch_stats_finalize(reinterpret_cast<const float2*>(stat_parts), parts, reinterpret_cast<float2*>(stats), M, D,
+                               eps, as_stream(stream));
+}
+
 int stad_attention(const void* qkv, void* out, int B, int H, int S, float scale, stad_stream_t stream) {
   return launch_attention(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), B, H, S, scale, as_stream(stream));
 }
@@ -276,14 +318,19 @@ int stad_vit_forward(const stad_model* m, const stad_input* in, const int32_t* t
   const int D = d->dim;
   int launches = 0;
 
-  // PatchEmbed + position table (mf:309-313 / mp:93-98)
-  if ((rc = patch_embed_impl(in, m->w_patch, m->pos_bias, tok_idx, ws.x, ws.gather, d, B, n_tok, stream, &launches)))
+  // PatchEmbed + position table (mf:309-313 / mp:93-98).  Its epilogue also emits the LayerNorm partial sums of the
+  // rows it stores, as does every GEMM below that writes the residual stream: no separate statistics pass.
+  int parts = 0;
+  if ((rc = patch_embed_impl(in, m->w_patch, m->pos_bias, tok_idx, ws.x, ws.gather, d, B, n_tok, stream, &launches,
+                             ws.parts, &parts)))
     return rc;
+  const int parts_resid = gemm_stat_parts(M, D, false, nullptr);
 
   for (int l = 0; l < d->depth; ++l) {
     const stad_block& blk = m->blocks[l];
+    const bool last = l + 1 == d->depth;
     // x = x + proj(attn(norm1(x)))                                     (mf:161)
-    if ((rc = launch_row_stats(ws.x, ws.stats, M, D, m->eps, stream))) return rc;
+    if ((rc = launch_stats_finalize(ws.parts, parts, ws.stats, M, D, m->eps, stream))) return rc;
     GemmArgs q;
     q.a = ws.x; q.w = static_cast<const bf16*>(blk.w_qkv); q.M = M; q.N = 3 * D; q.K = D;
     q.epi = EPI_LN; q.bias = blk.b_qkv; q.colsum = blk.cs_qkv; q.stats = ws.stats; q.out = ws.qkv;
@@ -291,17 +338,19 @@ int stad_vit_forward(const stad_model* m, const stad_input* in, const int32_t* t
     if ((rc = launch_attention(ws.qkv, ws.attn, B, d->heads, n_tok, m->attn_scale, stream))) return rc;
     GemmArgs pr;
     pr.a = ws.attn; pr.w = static_cast<const bf16*>(blk.w_proj); pr.M = M; pr.N = D; pr.K = D;
-    pr.epi = EPI_RESID; pr.bias = blk.b_proj; pr.residual = ws.x; pr.out = ws.x;
+    pr.epi = EPI_RESID | EPI_STATS; pr.bias = blk.b_proj; pr.residual = ws.x; pr.out = ws.x; pr.stats_out = ws.parts;
     if ((rc = launch_gemm(pr, stream))) return rc;
+    parts = parts_resid;
     // x = x + fc2(gelu(fc1(norm2(x))))                                 (mf:162)
-    if ((rc = launch_row_stats(ws.x, ws.stats, M, D, m->eps, stream))) return rc;
+    if ((rc = launch_stats_finalize(ws.parts, parts, ws.stats, M, D, m->eps, stream))) return rc;
     GemmArgs f1;
     f1.a = ws.x; f1.w = static_cast<const bf16*>(blk.w_fc1); f1.M = M; f1.N = d->hidden; f1.K = D;
     f1.epi = EPI_LN | EPI_GELU; f1.bias = blk.b_fc1; f1.colsum = blk.cs_fc1; f1.stats = ws.stats; f1.out = ws.hidden;
     if ((rc = launch_gemm(f1, stream))) return rc;
     GemmArgs f2;
     f2.a = ws.hidden; f2.w = static_cast<const bf16*>(blk.w_fc2); f2.M = M; f2.N = D; f2.K = d->hidden;
-    f2.epi = EPI_RESID; f2.bias = blk.b_fc2; f2.residual = ws.x; f2.out = ws.x;
+    f2.epi = last ? EPI_RESID : (EPI_RESID | EPI_STATS); f2.bias = blk.b_fc2; f2.residual = ws.x; f2.out = ws.x;
+    f2.stats_out = last ? nullptr : ws.parts;
     if ((rc = launch_gemm(f2, stream))) return rc;
     launches += 7;
   }

@@ -49,6 +49,7 @@ struct KArgs {
   const float* bias;
   const float* colsum;
   const float2* stats;
+  float2* stats_out;
   const bf16* residual;
   const float* pos;
   const int32_t* tok_idx;
@@ -287,6 +288,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           rstd = st.y;
         }
       }
+      float st_sum = 0.f, st_sq = 0.f;  // EPI_STATS: running (sum, sumsq) of this thread's part of the row
       const float* pos_row = nullptr;
       if constexpr (EPI & EPI_POS) {
         if (row_ok) {
@@ -378,6 +380,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           o.z = pack_bf16(f[q * 8 + 4], f[q * 8 + 5]);
           o.w = pack_bf16(f[q * 8 + 6], f[q * 8 + 7]);
           my_row[q ^ swz] = o;
+          if constexpr (EPI & EPI_STATS) {
+            // statistics of the values as stored (bf16), which is what the next LayerNorm sees
+            const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float lo = bf16_lo(w[t]), hi = bf16_hi(w[t]);
+              st_sum += lo + hi;
+              st_sq = fmaf(lo, lo, fmaf(hi, hi, st_sq));
+            }
+          }
         }
         fence_proxy_async_smem();         // generic-proxy writes -> visible to the TMA (async proxy)
         named_bar_sync(1 + wg, 128);      // whole sub-tile staged
@@ -389,6 +401,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           __syncwarp();
         }
+      }
+      if constexpr (EPI & EPI_STATS) {
+        // one partial per (column tile, warpgroup), partial-major so that a warp's 32 rows are contiguous
+        if (row_ok)
+          p.stats_out[static_cast<size_t>(n_tile * 2 + wg) * p.M + row] = make_float2(st_sum, st_sq);
       }
     }
     if (lead_warp) {
@@ -412,7 +429,7 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
   using C = Cfg<BN>;
   const int tiles = ka.m_tiles * ka.n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  ProfScope prof(STAD_K_GEMM, EPI | (kPatch ? 16 : 0), ka.M, ka.N, ka.K, stream);
+  ProfScope prof(STAD_K_GEMM, EPI | (kPatch ? 32 : 0), ka.M, ka.N, ka.K, stream);
   gemm_kernel<BN, EPI, kPatch><<<grid, kThreads, C::SMEM_BYTES, stream>>>(ta, tb, to, tr, ka);
   STAD_LAUNCH_OK("gemm_kernel");
   return STAD_OK;
@@ -469,7 +486,15 @@ int gemm_init() {
   if ((rc = set_smem_all_bn<EPI_RESID, false>())) return rc;
   if ((rc = set_smem_all_bn<EPI_POS, false>())) return rc;
   if ((rc = set_smem_all_bn<EPI_POS, true>())) return rc;
+  if ((rc = set_smem_all_bn<EPI_RESID | EPI_STATS, false>())) return rc;
+  if ((rc = set_smem_all_bn<EPI_POS | EPI_STATS, false>())) return rc;
+  if ((rc = set_smem_all_bn<EPI_POS | EPI_STATS, true>())) return rc;
   return STAD_OK;
+}
+
+int gemm_stat_parts(int M, int N, bool patch, const PatchGeom* pg) {
+  const int m_tiles = patch ? (M / (pg->Tp * pg->Hp * pg->Wp)) * pg->Tp * pg->h_tiles : ceil_div(M, BM);
+  return 2 * (N / pick_bn(m_tiles, N));
 }
 
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
@@ -483,6 +508,9 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   if (g.epi & EPI_LN) STAD_CHECK_ARG(g.stats && g.colsum, "gemm: LN epilogue needs stats and colsum");
   if (g.epi & EPI_RESID) STAD_CHECK_ARG(g.residual, "gemm: residual epilogue needs a residual");
   if (g.epi & EPI_POS) STAD_CHECK_ARG(g.pos && (g.tok_idx || g.pos_rows > 0), "gemm: pos epilogue needs a table");
+  if (g.epi & EPI_STATS) STAD_CHECK_ARG(g.stats_out, "gemm: statistics epilogue needs an output buffer");
+  if ((reinterpret_cast<uintptr_t>(g.stats) | reinterpret_cast<uintptr_t>(g.stats_out)) & 7)
+    return fail(STAD_E_ALIGN, "gemm: statistics buffers must be 8-byte aligned");
 
   KArgs ka{};
   ka.M = g.M;
@@ -491,6 +519,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   ka.bias = g.bias;
   ka.colsum = g.colsum;
   ka.stats = g.stats;
+  ka.stats_out = g.stats_out;
   ka.residual = g.residual;
   ka.pos = g.pos;
   ka.tok_idx = g.tok_idx;
@@ -541,10 +570,13 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   }
 
   if (g.patch) {
-    STAD_CHECK_ARG(g.epi == EPI_POS, "gemm: patch mode supports only the pos epilogue");
+    STAD_CHECK_ARG((g.epi & ~EPI_STATS) == EPI_POS, "gemm: patch mode supports only the pos epilogue");
+    if (g.epi & EPI_STATS) return dispatch_bn<EPI_POS | EPI_STATS, true>(bn, ta, tb, to, tr, ka, stream);
     return dispatch_bn<EPI_POS, true>(bn, ta, tb, to, tr, ka, stream);
   }
   switch (g.epi) {
+    case EPI_RESID | EPI_STATS: return dispatch_bn<EPI_RESID | EPI_STATS, false>(bn, ta, tb, to, tr, ka, stream);
+    case EPI_POS | EPI_STATS: return dispatch_bn<EPI_POS | EPI_STATS, false>(bn, ta, tb, to, tr, ka, stream);
     case 0: return dispatch_bn<0, false>(bn, ta, tb, to, tr, ka, stream);
     case EPI_LN: return dispatch_bn<EPI_LN, false>(bn, ta, tb, to, tr, ka, stream);
     case EPI_LN | EPI_GELU: return dispatch_bn<EPI_LN | EPI_GELU, false>(bn, ta, tb, to, tr, ka, stream);

@@ -15,7 +15,13 @@ struct PatchGeom {
   int n_planes;             // extent of the plane dimension of the input tensor map
 };
 
-enum : int { EPI_LN = 1, EPI_GELU = 2, EPI_RESID = 4, EPI_POS = 8 };
+enum : int { EPI_LN = 1, EPI_GELU = 2, EPI_RESID = 4, EPI_POS = 8, EPI_STATS = 16 };
+
+// LayerNorm statistics without a pass over x: the epilogue of the GEMM that writes the residual stream x (patch embed,
+// attn.proj, mlp.fc2) emits, for every output row and every (column tile, epilogue warpgroup), (sum, sum of squares)
+// of the bf16 values it stored; launch_stats_finalize adds a row's partials in index order (deterministic, no atomics)
+// and writes (mean, rstd) for the following LN-folded GEMM (nn.LayerNorm statistics, modeling_finetune.py:143/149).
+constexpr int kMaxStatParts = 32;  // 2 * N / 64 at the narrowest column tile, N <= 1024
 
 struct GemmArgs {
   const bf16* a = nullptr;  // [M, K] (plain) or the bf16 plane tensor (patch mode)
@@ -25,6 +31,7 @@ struct GemmArgs {
   const float* bias = nullptr;       // [N] or null
   const float* colsum = nullptr;     // [N]   (EPI_LN)
   const float2* stats = nullptr;     // [M]   (EPI_LN) (mean, rstd)
+  float2* stats_out = nullptr;       // [2 * n_tiles, M] (EPI_STATS) partial (sum, sumsq) of the stored rows
   const bf16* residual = nullptr;    // [M,N] (EPI_RESID)
   const float* pos = nullptr;        // [pos_rows, N] (EPI_POS)
   const int32_t* tok_idx = nullptr;  // [M] row -> pos row, or null: pos row = m % pos_rows
@@ -34,12 +41,14 @@ struct GemmArgs {
 };
 
 int launch_gemm(const GemmArgs& g, cudaStream_t stream);
+int gemm_stat_parts(int M, int N, bool patch, const PatchGeom* pg);  // partials per row an EPI_STATS launch writes
 int gemm_init();  // raise dynamic smem limits
 
 int launch_attention(const bf16* qkv, bf16* out, int B, int H, int S, float scale, cudaStream_t stream);
 int attention_init();
 
 int launch_cast_f32_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream);
+int launch_stats_finalize(const float2* parts, int n_parts, float2* stats, int M, int D, float eps, cudaStream_t stream);
 int launch_row_stats(const bf16* x, float2* stats, int M, int D, float eps, cudaStream_t stream);
 int launch_layernorm(const bf16* x, const float* g, const float* b, float* y, int M, int D, float eps,
                      cudaStream_t stream);

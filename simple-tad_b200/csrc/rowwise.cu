@@ -112,6 +112,25 @@ row_norm_kernel(const bf16* __restrict__ x, float2* __restrict__ stats, const fl
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// (sum, sumsq) partials [n_parts, M] written by the statistics epilogue of the residual GEMMs -> (mean, rstd) [M].
+// One thread per row; partials are added in index order (deterministic).  Bytes: 8 M (n_parts + 1).
+__global__ void __launch_bounds__(256)
+stats_finalize_kernel(const float2* __restrict__ parts, int n_parts, float2* __restrict__ stats, int M, float inv_d,
+                      float eps) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < n_parts; ++i) {
+    const float2 v = __ldg(&parts[static_cast<size_t>(i) * M + row]);
+    s1 += v.x;
+    s2 += v.y;
+  }
+  const float mean = s1 * inv_d;
+  const float var = fmaxf(fmaf(-mean, mean, s2 * inv_d), 0.f);
+  stats[row] = make_float2(mean, rsqrtf(var + eps));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // mean-pool stage 1: grid (kPoolChunks, B); block sums its slice of the tokens for every column.
 // Bytes: 2 B N D read + 4 B kPoolChunks D written.  Deterministic (no atomics).
 constexpr int kPoolChunks = 16;
@@ -265,6 +284,17 @@ static int check_row_args(const void* x, int M, int D) {
   STAD_CHECK_ARG(D % 8 == 0 && D <= kMaxChunks * 256, "row kernel: D=%d must be a multiple of 8 and <= %d", D,
                  kMaxChunks * 256);
   if (reinterpret_cast<uintptr_t>(x) & 15) return fail(STAD_E_ALIGN, "row kernel: x must be 16-byte aligned");
+  return STAD_OK;
+}
+
+int launch_stats_finalize(const float2* parts, int n_parts, float2* stats, int M, int D, float eps, cudaStream_t stream) {
+  STAD_CHECK_ARG(M > 0 && D > 0 && n_parts >= 1 && n_parts <= kMaxStatParts, "stats_finalize: M=%d D=%d parts=%d", M, D,
+                 n_parts);
+  if ((reinterpret_cast<uintptr_t>(parts) | reinterpret_cast<uintptr_t>(stats)) & 7)
+    return fail(STAD_E_ALIGN, "stats_finalize: buffers must be 8-byte aligned");
+  ProfScope prof(STAD_K_ROW_STATS, 1, M, D, n_parts, stream);
+  stats_finalize_kernel<<<ceil_div(M, 256), 256, 0, stream>>>(parts, n_parts, stats, M, 1.0f / static_cast<float>(D), eps);
+  STAD_LAUNCH_OK("stats_finalize");
   return STAD_OK;
 }
 

@@ -231,8 +231,7 @@ class Block(nn.Module):
         st = _lib.row_stats(h, eps1)
         qkv = _lib.ln_gemm(h, st, pk["w_qkv"], pk["b_qkv"], pk["cs_qkv"])
         ctx = _lib.attention(qkv.view(B, N, 3, self.attn.num_heads, 64), scale=self.attn.scale)
-        h = _lib.gemm_bias_residual(ctx.view(B * N, D), pk["w_proj"], pk["b_proj"], residual=h)
-        st = _lib.row_stats(h, eps2)
+        h, st = _lib.gemm_bias_residual_stats(ctx.view(B * N, D), pk["w_proj"], pk["b_proj"], h, eps2)
         hid = _lib.ln_gemm(h, st, pk["w_fc1"], pk["b_fc1"], pk["cs_fc1"], gelu=True)
         h = _lib.gemm_bias_residual(hid, pk["w_fc2"], pk["b_fc2"], residual=h)
         return h.view(B, N, D).to(x.dtype)

@@ -126,6 +126,33 @@ def check_gemm(M=1568, N=768, K=768, mode="plain", seed=0):
     return _stats(out, ref, f"gemm.{mode}[{M}x{N}x{K}]", 2e-2, 1e-2)
 
 
+def check_gemm_stats(M=3136, D=768, N2=3072, K1=768, seed=0):
+    """residual GEMM whose epilogue emits the LayerNorm statistics of the rows it stores -> LN-folded GEMM, against
+    layer_norm(x) @ w2^T in fp32 on the bf16 x the first GEMM stored; the statistics also against the two-pass
+    statistics kernel."""
+    eps = 1e-6
+    a = _bf16(M, K1, seed=seed + 41)
+    w1 = _bf16(D, K1, seed=seed + 42, scale=0.05)
+    b1 = _f32(D, seed=seed + 43, scale=0.5)
+    res = (_f32(M, D, seed=seed + 44) + _f32(M, 1, seed=seed + 45, scale=2.0)).to(torch.bfloat16)  # per-row offset
+    x, st = L.gemm_bias_residual_stats(a, w1, b1, res, eps)
+    w2 = _bf16(N2, D, seed=seed + 46, scale=0.05)
+    b2 = _f32(N2, seed=seed + 47, scale=0.5)
+    colsum = w2.float().sum(1).contiguous()
+    y = L.ln_gemm(x, st, w2, b2, colsum, gelu=True)
+    st2 = L.row_stats(x, eps)
+    torch.cuda.synchronize()
+    xr = a.float() @ w1.float().t() + b1 + res.float()
+    r1 = _stats(x, xr, f"gemm_stats.x[{M}x{D}x{K1}]", 3e-2, 1e-2)
+    xf = x.float()
+    s1 = _stats(st[:, 0], xf.mean(1), "gemm_stats.mean", 1e-4, 1e-4)
+    s2 = _stats(st[:, 1], (xf.var(1, unbiased=False) + eps).rsqrt(), "gemm_stats.rstd", 1e-4, 2e-4)
+    s3 = _stats(st, st2, "gemm_stats vs row_stats kernel", 1e-4, 2e-4)
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(xf, (D,), None, None, eps) @ w2.float().t() + b2)
+    r2 = _stats(y, ref, f"gemm_stats.ln_gelu[{M}x{N2}x{D}]", 2e-2, 1e-2)
+    return {"name": "gemm_stats", "x": r1, "mean": s1, "rstd": s2, "vs_kernel": s3, "y": r2}
+
+
 # ------------------------------------------------------------------------------------------------------- attention
 def check_attention(B=2, H=3, S=1568, peaky=1.0, seed=0):
     qkv = _bf16(B, S, 3, H, 64, seed=seed + 21, scale=1.0)
@@ -197,6 +224,8 @@ CHECKS = {
     "gemm_resid": lambda: [check_gemm(3136, 768, 768, "resid"), check_gemm(1568 * 3, 1024, 4096, "resid")],
     "gemm_ln": lambda: [check_gemm(3136, 2304, 768, "ln"), check_gemm(1568, 1152, 384, "ln")],
     "gemm_ln_gelu": lambda: [check_gemm(3136, 3072, 768, "ln_gelu"), check_gemm(1568, 4096, 1024, "ln_gelu")],
+    "gemm_stats": lambda: [check_gemm_stats(3136, 768, 3072, 768), check_gemm_stats(1568, 384, 1152, 1536, seed=3),
+                           check_gemm_stats(200, 1024, 1024, 4096, seed=5)],
     "attention_small": lambda: check_attention(1, 1, 128),
     "attention_tail": lambda: [check_attention(1, 2, 160), check_attention(2, 1, 392)],
     "attention": lambda: [check_attention(2, 3, 1568), check_attention(1, 12, 1568, peaky=6.0)],

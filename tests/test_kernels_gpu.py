@@ -6,7 +6,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("name", [
     "cast", "row_stats", "layernorm", "pool_head", "gemm_plain_small", "gemm_plain_k", "gemm_plain", "gemm_bn",
-    "gemm_resid", "gemm_ln", "gemm_ln_gelu", "attention_small", "attention_tail", "attention", "attention_ragged", "attention_persistent", "patch_embed",
+    "gemm_resid", "gemm_ln", "gemm_ln_gelu", "gemm_stats", "attention_small", "attention_tail", "attention", "attention_ragged", "attention_persistent", "patch_embed",
     "patch_embed_frames", "patch_embed_masked",
 ])
 def test_kernel(name):

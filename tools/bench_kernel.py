@@ -48,6 +48,9 @@ def main():
         if mode in ("plain", "bias", "resid"):
             res = torch.randn(M, N, device="cuda").to(torch.bfloat16) if mode == "resid" else None
             fn = lambda: L.gemm_bias_residual(a, w, None if mode == "plain" else bias, res)  # noqa: E731
+        elif mode == "resid_stats":
+            res = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+            fn = lambda: L.gemm_bias_residual_stats(a, w, bias, res, 1e-6)  # noqa: E731
         else:
             stats = L.row_stats(a, 1e-6)
             colsum = w.float().sum(1).contiguous()
