@@ -269,6 +269,7 @@ def main():
         "peak_source": peaks["source"] + ", sustained cuBLAS bf16",
         "launches_per_step": gemm["launches"] / args.steps, "avg_launch_ms": gemm["ms"] / max(1, gemm["launches"]),
         "share_of_step": gemm["ms"] / total_kernel_ms,
+        "kernel_ms_per_step": total_kernel_ms / args.steps,  # sum of all event-timed launches; the rest is launch gaps
         "attention": {"achieved": att_tflops, "frac": att_tflops / peak, "share_of_step": att["ms"] / total_kernel_ms,
                       "avg_launch_ms": att["ms"] / max(1, att["launches"])},
         "other_share_of_step": {k: v["ms"] / total_kernel_ms for k, v in by_kind.items() if k not in ("gemm", "attention")},

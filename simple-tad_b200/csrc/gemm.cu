@@ -318,28 +318,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         const int n0 = n_tile * BN + wg * COLS + c * kSubCols;
         if constexpr (EPI & EPI_LN) {
+          // rstd * (acc - mean * colsum) + bias  as two packed FMAs per column pair
+          const float nmean = -mean;
+          const bool has_bias = p.bias != nullptr;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 cs = __ldg(reinterpret_cast<const float4*>(p.colsum + n0 + j));
-            f[j + 0] = rstd * fmaf(-mean, cs.x, f[j + 0]);
-            f[j + 1] = rstd * fmaf(-mean, cs.y, f[j + 1]);
-            f[j + 2] = rstd * fmaf(-mean, cs.z, f[j + 2]);
-            f[j + 3] = rstd * fmaf(-mean, cs.w, f[j + 3]);
+            const float4 bv = has_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            fma2(f[j + 0], f[j + 1], cs.x, cs.y, nmean, nmean, f[j + 0], f[j + 1]);
+            fma2(f[j + 2], f[j + 3], cs.z, cs.w, nmean, nmean, f[j + 2], f[j + 3]);
+            fma2(f[j + 0], f[j + 1], f[j + 0], f[j + 1], rstd, rstd, bv.x, bv.y);
+            fma2(f[j + 2], f[j + 3], f[j + 2], f[j + 3], rstd, rstd, bv.z, bv.w);
           }
-        }
-        if (p.bias != nullptr) {
+        } else if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-            f[j + 0] += bv.x;
-            f[j + 1] += bv.y;
-            f[j + 2] += bv.z;
-            f[j + 3] += bv.w;
+            add2(f[j + 0], f[j + 1], f[j + 0], f[j + 1], bv.x, bv.y);
+            add2(f[j + 2], f[j + 3], f[j + 2], f[j + 3], bv.z, bv.w);
           }
         }
         if constexpr (EPI & EPI_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1], f[j], f[j + 1]);
         }
         if constexpr (EPI & EPI_POS) {
           if (row_ok) {

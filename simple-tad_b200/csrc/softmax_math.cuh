@@ -16,19 +16,6 @@ STAD_DEVICE float max3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-// packed two-lane fp32 math (FFMA2 / FADD2)
-STAD_DEVICE void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
-}
-STAD_DEVICE void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d0), "=f"(d1)
-      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
 STAD_DEVICE float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
