@@ -100,6 +100,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(model_name, B, world, sample=None):
+    """`config` of both arms: the workload BASELINE.json's metric is quoted on (config 2)."""
+    from oracle import synth
+    D = synth.ARCHS[model_name][0]
+    cfg = {"workload": f"{model_name} 16x224^2 frame-level sliding-window inference, {B} stride-1 windows "
+                       f"(one {B + 15}-frame DoTA-shaped synthetic video chunk) per step per GPU, 2-class head",
+           "batch_per_gpu": B, "parallelism": f"clip-sharded x{world}, one score gather",
+           "l2": f"inputs rotate over 4 distinct videos; activations per step ({B * 1568 * D * 2 * 5 / 1e6:.0f} MB) "
+                 "exceed the 126 MB L2"}
+    if sample:
+        cfg["sample"] = sample
+    return cfg
+
+
 def cpu_forward_setup(model_name):
     """The reference algorithm on the CPU (oracle/ = restatement of modeling_finetune.py pinned by tests/golden)."""
     from oracle import synth, vit_oracle
@@ -142,11 +156,12 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = args.ref_clips * args.steps / dt
     line = {
-        "impl": "reference", "metric": "clips/sec (16x224^2)", "value": value, "unit": "clips/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": "clips/sec (16x224^2 bf16)", "value": value, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} 16x224^2 2-class forward, {args.ref_clips} clip(s) per step on the host CPU",
-                   "l2": "n/a (CPU)"},
+        "config": workload_config(args.model, args.batch, args.gpus,
+                                  sample=f"bounded sample: {args.ref_clips} clip(s) of the workload per step, fp32, on the "
+                                         f"host CPU ({torch.get_num_threads()} threads); rank 0 only"),
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": f"{args.steps} steps x {args.ref_clips} clip(s), oracle/vit_oracle.py fp32, "
                                    f"{torch.get_num_threads()} threads"},
@@ -297,11 +312,7 @@ def main():
         "metric": "clips/sec (16x224^2 bf16)", "value": clips_per_s, "unit": "clips/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.model} 16x224^2 frame-level sliding-window inference, {B} stride-1 windows "
-                               f"(one {T_frames}-frame DoTA-shaped synthetic video chunk) per step per GPU, 2-class head",
-                   "batch_per_gpu": B, "parallelism": f"clip-sharded x{world}, one score gather",
-                   "l2": f"inputs rotate over {n_bufs} distinct videos; activations per step "
-                         f"({B * 1568 * D * 2 * 5 / 1e6:.0f} MB) exceed the 126 MB L2"},
+        "config": workload_config(args.model, B, world),
         "model_tflops_per_gpu": model_tflops,
         "model_frac_of_peak": {"measured_sustained": model_tflops / peaks["bf16_tflops_sustained"],
                                "measured_burst": model_tflops / peaks["bf16_tflops"], "spec_2250": model_tflops / 2250.0},
