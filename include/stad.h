@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define STAD_ABI_VERSION 2
+#define STAD_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define STAD_API __attribute__((visibility("default")))
@@ -106,6 +106,24 @@ typedef struct stad_model {
   float attn_scale;    /* head_dim ** -0.5 (mf:67) */
 } stad_model;
 
+/* PretrainVisionTransformer (mp:183-291) after weight preparation: encoder (visible tokens) -> encoder_to_decoder ->
+ * decoder over all N tokens -> pixel head on the masked tokens.  The encoder's `norm` (mp:59,107) is folded into
+ * encoder_to_decoder and the decoder's `norm` (mp:143,174) into the pixel head, exactly like norm1/norm2 in stad_block. */
+typedef struct stad_mae_model {
+  stad_model encoder;       /* dims.num_classes = 0; norm_g / norm_b / w_head / b_head are not read here             */
+  stad_dims dec_dims;       /* dim = D_dec (192 / 384 / 512), depth, heads, hidden; num_classes = 1536 pixel values;
+                               geometry fields as the encoder's                                                      */
+  const void* w_e2d;        /* [D_dec, D_enc] bf16 = encoder_to_decoder.weight diag(norm.weight)   (mp:253, mp:281)  */
+  const float* b_e2d;       /* [D_dec] = encoder_to_decoder.weight norm.bias   (the Linear itself has no bias)       */
+  const float* cs_e2d;      /* [D_dec] column sums of w_e2d                                                          */
+  const float* pos_dec;     /* [N, D_dec] fp32 sinusoid table of the decoder width                 (mp:257)          */
+  const float* mask_token;  /* [D_dec] fp32                                                        (mp:255)          */
+  const stad_block* dec_blocks; /* HOST array of dec_dims.depth entries                            (mp:133-139)      */
+  const void* w_pix;        /* [1536, D_dec] bf16 = decoder.head.weight diag(decoder.norm.weight)  (mp:143-144)      */
+  const float* b_pix;       /* [1536] = decoder.head.bias + decoder.head.weight decoder.norm.bias                    */
+  const float* cs_pix;      /* [1536] */
+} stad_mae_model;
+
 /* Where stad_vit_forward writes its results; any pointer may be NULL (nothing is written for it). */
 typedef struct stad_outputs {
   float* logits;   /* [B, num_classes]  head output, mf:334                                   (classifier models) */
@@ -126,7 +144,8 @@ STAD_API const char* stad_last_error(void);
  * Not CUDA-graph capturable; leave disabled (the default) outside benchmarks. */
 enum {
   STAD_K_CAST = 0, STAD_K_GATHER = 1, STAD_K_GEMM = 2, STAD_K_ATTENTION = 3, STAD_K_ROW_STATS = 4,
-  STAD_K_LAYERNORM = 5, STAD_K_POOL = 6 /* ROW_STATS with epi = 1: stad_stats_finalize */
+  STAD_K_LAYERNORM = 5, STAD_K_POOL = 6, /* ROW_STATS with epi = 1: stad_stats_finalize */
+  STAD_K_ASSEMBLE = 7, STAD_K_TAIL = 8, STAD_K_NORMALIZE = 9
 };
 typedef struct stad_profile_record {
   int32_t kind;    /* STAD_K_*                                                        */
@@ -205,6 +224,38 @@ STAD_API size_t stad_workspace_bytes(const stad_dims* dims, int B, int n_tok);
  * Returns the number of kernels launched (>= 0) or a negative error. */
 STAD_API int stad_vit_forward(const stad_model* model, const stad_input* in, const int32_t* tok_idx, int B, int n_tok,
                      const stad_outputs* out, void* workspace, size_t workspace_bytes, stad_stream_t stream);
+
+/* ---- MAE pre-training forward (DAPT) ---------------------------------------------------------------------------- */
+/* Decoder input of PretrainVisionTransformer.forward (mp:283-288):
+ *   x_full[b, i] = vis[b, i]                                   for i <  n_vis  (x_vis + pos_emd_vis, the position rows
+ *                                                              are added by the encoder_to_decoder GEMM epilogue)
+ *   x_full[b, i] = mask_token + pos[mask_idx[b, i - n_vis]]    for i >= n_vis  (mask_token + pos_emd_mask)
+ * plus the LayerNorm statistics (mean, rstd) of every row of x_full (norm1 of the first decoder block).
+ * vis[B, n_vis, D] bf16, pos[N, D] fp32, mask_token[D] fp32, mask_idx int32[B, N - n_vis] (ids of the masked tokens in
+ * row-major order = what expand_pos_embed[mask] keeps), x_full[B, N, D] bf16, stats float[B*N, 2]. */
+STAD_API int stad_decoder_assemble(const void* vis, const float* pos, const float* mask_token, const int32_t* mask_idx,
+                                   void* x_full, float* stats, int B, int N, int n_vis, int D, float eps,
+                                   stad_stream_t stream);
+
+/* y[B, n_keep, C] fp32 = last n_keep rows of every clip of x[B, N, C] bf16: `x[:, -return_token_num:]`, mp:174. */
+STAD_API int stad_tail_rows_f32(const void* x, float* y, int B, int N, int n_keep, int C, stad_stream_t stream);
+
+STAD_API size_t stad_mae_workspace_bytes(const stad_mae_model* model, int B, int n_vis);
+
+/* PretrainVisionTransformer.forward(x, mask) (mp:276-291): pixels[B, N - n_vis, 1536] fp32, the decoder's predictions
+ * for the masked tokens of every clip in row-major token order.  vis_idx int32[B, n_vis]: ids of the visible tokens
+ * (x[~mask], mp:98); mask_idx int32[B, N - n_vis]: ids of the masked tokens (x[mask]); both row-major per clip.
+ * Returns the number of kernels launched (>= 0) or a negative error. */
+STAD_API int stad_mae_forward(const stad_mae_model* model, const stad_input* in, const int32_t* vis_idx,
+                              const int32_t* mask_idx, int B, int n_vis, float* pixels, void* workspace, size_t workspace_bytes, stad_stream_t stream);
+
+/* ---- frame preparation ------------------------------------------------------------------------------------------- */
+/* uint8 HWC frames [F, H, W, 3] (bgr != 0: channel order of cv2.imread; 0: RGB) -> bf16 planes [F, 3, H, W] (RGB)
+ *   = (v / 255 - mean[c]) / std[c].   prepare_image ri:15-34 (cvtColor + div 255 + normalise);  dota.py:357 +
+ *   volume_transforms.ClipToTensor / video_transforms.normalize on the dataset path.
+ * mean / std: HOST float[3] (RGB order).  The output is the frame buffer stad_input (STAD_IN_FRAMES) reads. */
+STAD_API int stad_normalize_frames_u8(const void* frames_u8, void* out_bf16, int F, int H, int W, const float* mean,
+                                      const float* std, int bgr, stad_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 from oracle import synth, vit_oracle  # noqa: E402
 
 HID_TOK = [0, 1, 13, 195, 196, 783, 1000, 1567]   # sampled tokens of the 1568
+PIX_TOK_STEP, PIX_VAL_STEP = 11, 6               # pretrain fixtures keep pixels[:, ::11, ::6]
 HID_CH = [0, 1, 2, 63, 64, 191, 255, 383]         # sampled channels (valid for D >= 384)
 
 
@@ -173,6 +174,50 @@ def gen_encoder(name, arch, B, ratio=0.9, seed=0):
          mask=mask.numpy(), meta=np.array([seed, B, ratio]))
 
 
+def gen_pretrain(name, arch, B, ratio=0.9, seed=0, decoder_depth=4):
+    """Full PretrainVisionTransformer (encoder + decoder, mp:183-291) of the unmodified reference."""
+    import modeling_pretrain as mp
+    from functools import partial
+    D, depth, heads = synth.ARCHS[arch]
+    Dd, dheads = synth.DECODERS[arch]
+    sd = synth.make_pretrain_state_dict(arch, seed=seed, decoder_depth=decoder_depth)
+    model = mp.PretrainVisionTransformer(
+        img_size=224, patch_size=16, encoder_embed_dim=D, encoder_depth=depth, encoder_num_heads=heads,
+        encoder_num_classes=0, decoder_num_classes=1536, decoder_embed_dim=Dd, decoder_num_heads=dheads,
+        decoder_depth=decoder_depth, mlp_ratio=4, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+        use_flash_attn=False)   # the kwargs of the factories mp:293-363 (+ decoder_depth, run_mae_pretraining.py)
+    res = model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    model.eval()
+    x = synth.make_clips(B, seed=seed)
+    mask = synth.tube_mask(B, ratio, seed=seed)
+    t0 = time.time()
+    with torch.no_grad():
+        y = model(x, mask)
+    print(f"{name}: reference pretrain {arch} {tuple(x.shape)} mask {ratio} -> {tuple(y.shape)} in {time.time() - t0:.1f}s")
+    o = vit_oracle.pretrain_forward(sd, x, mask, heads, dheads)
+    print(f"  oracle vs reference: max|d| = {(o - y).abs().max():.3e} (|y| max {y.abs().max():.3f})")
+    # sampled tokens x sampled pixel values in fp32 + the norm of EVERY predicted token (keeps the fixture small)
+    save(name, pixels_sample=y[:, ::PIX_TOK_STEP, ::PIX_VAL_STEP].numpy(), pixel_norm=y.norm(dim=-1).numpy(),
+         pixel_mean=y.mean(dim=1).numpy(), mask=mask.numpy(), meta=np.array([seed, B, ratio, decoder_depth]))
+
+
+def gen_masks(name):
+    """TubeMaskingGenerator of the unmodified reference (masking_generator.py) under fixed np.random seeds."""
+    import masking_generator as mg
+    out = {}
+    for seed, ratio in ((0, 0.9), (1, 0.75), (2, 0.5)):
+        np.random.seed(seed)
+        gen = mg.TubeMaskingGenerator((8, 14, 14), ratio)
+        out[f"mask_s{seed}"] = np.stack([gen() for _ in range(3)])
+        out[f"ratio_s{seed}"] = np.array(ratio)
+        np.random.seed(seed)
+        mine = np.stack([vit_oracle.TubeMaskingGenerator((8, 14, 14), ratio)() for _ in range(3)])
+        assert np.array_equal(mine, out[f"mask_s{seed}"]), "oracle TubeMaskingGenerator differs from the reference"
+    print(f"{name}: reference TubeMaskingGenerator, 3 seeds x 3 draws; oracle restatement identical")
+    save(name, **out)
+
+
 def main():
     install_shims()
     torch.set_num_threads(os.cpu_count())
@@ -184,6 +229,8 @@ def main():
     if on("small"):
         gen_classifier("small_vits_d2_b2", "vit_small_d2", B=2, seed=11)
         gen_encoder("small_enc_vitb_d2_b2", "vit_base_d2", B=2, seed=12)
+        gen_pretrain("small_mae_vits_d2_b2", "vit_small_d2", B=2, seed=14, decoder_depth=2)
+        gen_masks("tube_masks")
     if on("peaky"):
         gen_classifier("peaky_vits_d2_b2", "vit_small_d2", B=2, seed=13, peaky=3.0)
     # the five BASELINE.json configs
@@ -195,6 +242,8 @@ def main():
         gen_classifier("c3_vitl_2x20", "vit_large_patch16_224", video_T=20, n_videos=2, seed=3)
     if on("c4"):
         gen_encoder("c4_enc_vitb_b4", "vit_base_patch16_224", B=4, seed=4)
+    if on("mae"):
+        gen_pretrain("c4_mae_vitb_b2", "vit_base_patch16_224", B=2, seed=6, decoder_depth=4)
     if on("c5"):
         gen_classifier("c5_vitb_b8", "vit_base_patch16_224", B=8, seed=5)
 

@@ -19,6 +19,12 @@ ARCHS = {
     "vit_small_d2": (384, 2, 6),
     "vit_base_d2": (768, 2, 12),
 }
+DECODERS = {
+    # encoder arch -> (decoder_embed_dim, decoder_num_heads)   factories modeling_pretrain.py:293-363
+    "vit_small_patch16_224": (192, 3), "vit_small_d2": (192, 3),
+    "vit_base_patch16_224": (384, 6), "vit_base_d2": (384, 6),
+    "vit_large_patch16_224": (512, 8),
+}
 PRETRAIN_ARCHS = {
     # encoders of modeling_pretrain.py:293-387
     "pretrain_videomae_small_patch16_224": "vit_small_patch16_224",
@@ -78,6 +84,42 @@ def make_state_dict(arch, seed=0, num_classes=2, encoder=False, peaky=1.0):
         # head wide enough that the two logits differ by O(1): p is neither 0.5 nor saturated
         sd["head.weight"] = 0.05 * torch.randn((num_classes, D), generator=g)
         sd["head.bias"] = 0.1 * torch.randn((num_classes,), generator=g)
+    return sd
+
+
+def _block_weights(sd, p, D, g):
+    sd[p + "norm1.weight"] = 1.0 + 0.1 * torch.randn((D,), generator=g)
+    sd[p + "norm1.bias"] = 0.05 * torch.randn((D,), generator=g)
+    sd[p + "attn.q_bias"] = 0.02 * torch.randn((D,), generator=g)
+    sd[p + "attn.v_bias"] = 0.02 * torch.randn((D,), generator=g)
+    sd[p + "attn.qkv.weight"] = _trunc_normal((3 * D, D), 0.04, g)
+    sd[p + "attn.proj.weight"] = _trunc_normal((D, D), 0.04, g)
+    sd[p + "attn.proj.bias"] = 0.02 * torch.randn((D,), generator=g)
+    sd[p + "norm2.weight"] = 1.0 + 0.1 * torch.randn((D,), generator=g)
+    sd[p + "norm2.bias"] = 0.05 * torch.randn((D,), generator=g)
+    sd[p + "mlp.fc1.weight"] = _trunc_normal((4 * D, D), 0.04, g)
+    sd[p + "mlp.fc1.bias"] = 0.02 * torch.randn((4 * D,), generator=g)
+    sd[p + "mlp.fc2.weight"] = _trunc_normal((D, 4 * D), 0.04, g)
+    sd[p + "mlp.fc2.bias"] = 0.02 * torch.randn((D,), generator=g)
+
+
+def make_pretrain_state_dict(arch, seed=0, decoder_depth=4):
+    """State dict of PretrainVisionTransformer (modeling_pretrain.py:183-258) for the encoder `arch`:
+    encoder.* (as make_state_dict(encoder=True)), decoder.{blocks.*, norm.*, head.*}, encoder_to_decoder.weight,
+    mask_token — all non-trivial so every bias / affine path is exercised."""
+    D, _, _ = ARCHS[arch]
+    Dd, _ = DECODERS[arch]
+    sd = {"encoder." + k: v for k, v in make_state_dict(arch, seed=seed, encoder=True).items()}
+    g = _gen(5000 + seed)
+    for i in range(decoder_depth):
+        _block_weights(sd, f"decoder.blocks.{i}.", Dd, g)
+    sd["decoder.norm.weight"] = 1.0 + 0.1 * torch.randn((Dd,), generator=g)
+    sd["decoder.norm.bias"] = 0.05 * torch.randn((Dd,), generator=g)
+    n_pix = CHANS * TUBELET * PATCH * PATCH
+    sd["decoder.head.weight"] = _trunc_normal((n_pix, Dd), 0.05, g)
+    sd["decoder.head.bias"] = 0.05 * torch.randn((n_pix,), generator=g)
+    sd["encoder_to_decoder.weight"] = _trunc_normal((Dd, D), 0.04, g)
+    sd["mask_token"] = 0.5 * torch.randn((1, 1, Dd), generator=g)
     return sd
 
 

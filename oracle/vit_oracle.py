@@ -97,6 +97,54 @@ def encoder_forward(sd, x, mask, heads):
     return F.layer_norm(h, (D,), sd["norm.weight"], sd["norm.bias"], LN_EPS)  # mp:107
 
 
+def _sub(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+@torch.no_grad()
+def decoder_forward(sd, x, return_token_num, heads):
+    """PretrainVisionTransformerDecoder.forward, mp:164-178: blocks, then head(norm(.)) on the LAST return_token_num
+    tokens (all tokens if <= 0).  sd: the decoder's own state dict (blocks.*, norm.*, head.*)."""
+    D = sd["norm.weight"].shape[0]
+    for i in range(_depth(sd)):
+        x = block(sd, i, x, heads)
+    if return_token_num > 0:
+        x = x[:, -return_token_num:]                                   # mp:174
+    return F.linear(F.layer_norm(x, (D,), sd["norm.weight"], sd["norm.bias"], LN_EPS), sd["head.weight"], sd["head.bias"])
+
+
+@torch.no_grad()
+def pretrain_forward(sd, x, mask, enc_heads, dec_heads):
+    """PretrainVisionTransformer.forward, mp:276-291.  sd: full state dict (encoder.*, decoder.*,
+    encoder_to_decoder.weight, mask_token).  Returns [B, N_mask, 1536]: predicted pixels of the masked tokens."""
+    x_vis = encoder_forward(_sub(sd, "encoder."), x, mask, enc_heads)  # mp:278  [B, N_vis, C_e]
+    x_vis = F.linear(x_vis, sd["encoder_to_decoder.weight"])          # mp:281  (no bias, mp:253)
+    B, _, C = x_vis.shape
+    pos = sinusoid_table(mask.shape[1], C).expand(B, -1, -1)           # mp:257, mp:285
+    pos_vis = pos[~mask].reshape(B, -1, C)                             # mp:286
+    pos_mask = pos[mask].reshape(B, -1, C)                             # mp:287
+    x_full = torch.cat([x_vis + pos_vis, sd["mask_token"] + pos_mask], dim=1)  # mp:288
+    return decoder_forward(_sub(sd, "decoder."), x_full, pos_mask.shape[1], dec_heads)  # mp:289
+
+
+class TubeMaskingGenerator:
+    """masking_generator.py:3-23 restated: one shuffled per-frame mask of int(ratio * H*W) ones, tiled over the
+    temporal slots; drawn with np.random exactly as the reference does (same draws for the same np.random.seed)."""
+
+    def __init__(self, input_size, mask_ratio):
+        self.frames, self.height, self.width = input_size
+        self.num_patches_per_frame = self.height * self.width
+        self.total_patches = self.frames * self.num_patches_per_frame
+        self.num_masks_per_frame = int(mask_ratio * self.num_patches_per_frame)
+        self.total_masks = self.frames * self.num_masks_per_frame
+
+    def __call__(self):
+        per_frame = np.hstack([np.zeros(self.num_patches_per_frame - self.num_masks_per_frame),
+                               np.ones(self.num_masks_per_frame)])
+        np.random.shuffle(per_frame)
+        return np.tile(per_frame, (self.frames, 1)).flatten()
+
+
 def visible_indices(mask):
     """Row-major indices of the surviving tokens of each clip (what x[~mask] keeps, mp:98): int32 [B, n_vis]."""
     B = mask.shape[0]

@@ -17,7 +17,8 @@ EXPORTS = (
     "stad_abi_version", "stad_init", "stad_last_error", "stad_cast_f32_bf16", "stad_row_stats", "stad_layernorm",
     "stad_pool_norm_head", "stad_patch_embed", "stad_ln_gemm", "stad_gemm_bias_residual", "stad_attention",
     "stad_workspace_bytes", "stad_vit_forward", "stad_profile_enable", "stad_profile_read", "stad_stat_parts",
-    "stad_gemm_bias_residual_stats", "stad_stats_finalize",
+    "stad_gemm_bias_residual_stats", "stad_stats_finalize", "stad_decoder_assemble", "stad_tail_rows_f32",
+    "stad_mae_workspace_bytes", "stad_mae_forward", "stad_normalize_frames_u8",
 )
 
 
@@ -42,6 +43,13 @@ class StadModel(C.Structure):
                 ("eps", C.c_float), ("attn_scale", C.c_float)]
 
 
+class StadMaeModel(C.Structure):
+    _fields_ = [("encoder", StadModel), ("dec_dims", StadDims), ("w_e2d", C.c_void_p), ("b_e2d", C.c_void_p),
+                ("cs_e2d", C.c_void_p), ("pos_dec", C.c_void_p), ("mask_token", C.c_void_p),
+                ("dec_blocks", C.POINTER(StadBlock)), ("w_pix", C.c_void_p), ("b_pix", C.c_void_p),
+                ("cs_pix", C.c_void_p)]
+
+
 class StadOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("logits", "probs", "features", "tokens")]
 
@@ -51,7 +59,8 @@ class StadProfileRecord(C.Structure):
                 ("ms", C.c_float)]
 
 
-KIND_NAMES = {0: "cast", 1: "gather", 2: "gemm", 3: "attention", 4: "row_stats", 5: "layernorm", 6: "pool"}
+KIND_NAMES = {0: "cast", 1: "gather", 2: "gemm", 3: "attention", 4: "row_stats", 5: "layernorm", 6: "pool",
+              7: "assemble", 8: "tail", 9: "normalize"}
 
 _lib = None
 _inited_devices = set()
@@ -88,6 +97,12 @@ def load():
         "stad_profile_read": (C.c_int, [C.POINTER(StadProfileRecord), i32]),
         "stad_vit_forward": (C.c_int, [C.POINTER(StadModel), C.POINTER(StadInput), vp, i32, i32,
                                        C.POINTER(StadOutputs), vp, sz, vp]),
+        "stad_decoder_assemble": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp]),
+        "stad_tail_rows_f32": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+        "stad_mae_workspace_bytes": (sz, [C.POINTER(StadMaeModel), i32, i32]),
+        "stad_mae_forward": (C.c_int, [C.POINTER(StadMaeModel), C.POINTER(StadInput), vp, vp, i32, i32, vp, vp, sz, vp]),
+        "stad_normalize_frames_u8": (C.c_int, [vp, vp, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), i32,
+                                               vp]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -287,4 +302,50 @@ def patch_embed(x, w, pos_bias, dims, B, n_tok, tok_idx=None, mode=STAD_IN_CLIPS
     inp = make_input(x, mode, n_frames, start, stride)
     check(load().stad_patch_embed(C.byref(inp), ptr(w), ptr(pos_bias), ptr(tok_idx), ptr(out), ptr(gather),
                                   C.byref(dims), B, n_tok, stream_ptr()), "stad_patch_embed")
+    return out
+
+
+def decoder_assemble(vis, pos, mask_token, mask_idx, n_tokens, eps):
+    """vis [B, n_vis, D] bf16 (x_vis + pos), pos [N, D] fp32, mask_token [D] fp32, mask_idx int32 [B, N - n_vis]
+    -> (x_full [B, N, D] bf16, stats [B*N, 2] fp32)   (mp:283-288)."""
+    init(vis.device)
+    _req(vis, torch.bfloat16, "vis")
+    _req(pos, torch.float32, "pos")
+    _req(mask_token, torch.float32, "mask_token")
+    _req(mask_idx, torch.int32, "mask_idx")
+    B, n_vis, D = vis.shape
+    N = int(n_tokens)
+    if tuple(mask_idx.shape) != (B, N - n_vis) or tuple(pos.shape) != (N, D) or mask_token.numel() != D:
+        raise ValueError(f"decoder_assemble: vis {tuple(vis.shape)}, pos {tuple(pos.shape)}, mask_idx {tuple(mask_idx.shape)}")
+    x = torch.empty(B, N, D, dtype=torch.bfloat16, device=vis.device)
+    stats = torch.empty(B * N, 2, dtype=torch.float32, device=vis.device)
+    check(load().stad_decoder_assemble(ptr(vis), ptr(pos), ptr(mask_token), ptr(mask_idx), ptr(x), ptr(stats), B, N,
+                                       n_vis, D, float(eps), stream_ptr()), "stad_decoder_assemble")
+    return x, stats
+
+
+def tail_rows_f32(x, n_keep):
+    """x [B, N, C] bf16 -> x[:, -n_keep:] as fp32 [B, n_keep, C]   (mp:174)."""
+    init(x.device)
+    _req(x, torch.bfloat16, "x")
+    B, N, Cc = x.shape
+    y = torch.empty(B, n_keep, Cc, dtype=torch.float32, device=x.device)
+    check(load().stad_tail_rows_f32(ptr(x), ptr(y), B, N, int(n_keep), Cc, stream_ptr()), "stad_tail_rows_f32")
+    return y
+
+
+def normalize_frames_u8(frames, mean, std, bgr=False, out=None):
+    """uint8 frames [F, H, W, 3] (HWC, as cv2 delivers them) -> bf16 planes [F, 3, H, W] = (v/255 - mean) / std, RGB
+    order   (prepare_image, ri:15-34)."""
+    init(frames.device)
+    _req(frames, torch.uint8, "frames")
+    if frames.dim() != 4 or frames.shape[3] != 3:
+        raise ValueError(f"normalize_frames_u8: expected [F, H, W, 3] uint8, got {tuple(frames.shape)}")
+    F_, H, W, _ = frames.shape
+    if out is None:
+        out = torch.empty(F_, 3, H, W, dtype=torch.bfloat16, device=frames.device)
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    sd = (C.c_float * 3)(*[float(v) for v in std])
+    check(load().stad_normalize_frames_u8(ptr(frames), ptr(out), F_, H, W, m, sd, int(bool(bgr)), stream_ptr()),
+          "stad_normalize_frames_u8")
     return out

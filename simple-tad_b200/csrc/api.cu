@@ -158,6 +158,78 @@ int patch_embed_impl(const stad_input* in, const void* w, const float* pos_bias,
   return STAD_OK;
 }
 
+
+// The transformer stack: `depth` x Block.forward (mf:159-162) over the residual stream ws.x [B * n_tok, D].
+//   parts_in > 0 : ws.parts holds that many LayerNorm partial sums per row of ws.x (written by the GEMM that produced x)
+//   parts_in == 0: ws.stats already holds (mean, rstd) of ws.x (e.g. written by launch_decoder_assemble)
+//   final_stats  : the last fc2 also emits partial sums (a LayerNorm-folded GEMM follows the stack); on return
+//                  ws.parts holds gemm_stat_parts(M, D) partials per row.
+int run_blocks(const stad_block* blocks, const stad_dims* d, float eps, float attn_scale, const Workspace& ws, int B,
+               int n_tok, int parts_in, bool final_stats, cudaStream_t stream, int* launches) {
+  const int M = B * n_tok;
+  const int D = d->dim;
+  const int parts_resid = gemm_stat_parts(M, D, false, nullptr);
+  int parts = parts_in;
+  int rc;
+  for (int l = 0; l < d->depth; ++l) {
+    const stad_block& blk = blocks[l];
+    const bool last = l + 1 == d->depth;
+    const bool emit = !last || final_stats;
+    // x = x + proj(attn(norm1(x)))                                     (mf:161)
+    if (parts > 0) {
+      if ((rc = launch_stats_finalize(ws.parts, parts, ws.stats, M, D, eps, stream))) return rc;
+      ++*launches;
+    }
+    GemmArgs q;
+    q.a = ws.x; q.w = static_cast<const bf16*>(blk.w_qkv); q.M = M; q.N = 3 * D; q.K = D;
+    q.epi = EPI_LN; q.bias = blk.b_qkv; q.colsum = blk.cs_qkv; q.stats = ws.stats; q.out = ws.qkv;
+    if ((rc = launch_gemm(q, stream))) return rc;
+    if ((rc = launch_attention(ws.qkv, ws.attn, B, d->heads, n_tok, attn_scale, stream))) return rc;
+    GemmArgs pr;
+    pr.a = ws.attn; pr.w = static_cast<const bf16*>(blk.w_proj); pr.M = M; pr.N = D; pr.K = D;
+    pr.epi = EPI_RESID | EPI_STATS; pr.bias = blk.b_proj; pr.residual = ws.x; pr.out = ws.x; pr.stats_out = ws.parts;
+    if ((rc = launch_gemm(pr, stream))) return rc;
+    parts = parts_resid;
+    // x = x + fc2(gelu(fc1(norm2(x))))                                 (mf:162)
+    if ((rc = launch_stats_finalize(ws.parts, parts, ws.stats, M, D, eps, stream))) return rc;
+    GemmArgs f1;
+    f1.a = ws.x; f1.w = static_cast<const bf16*>(blk.w_fc1); f1.M = M; f1.N = d->hidden; f1.K = D;
+    f1.epi = EPI_LN | EPI_GELU; f1.bias = blk.b_fc1; f1.colsum = blk.cs_fc1; f1.stats = ws.stats; f1.out = ws.hidden;
+    if ((rc = launch_gemm(f1, stream))) return rc;
+    GemmArgs f2;
+    f2.a = ws.hidden; f2.w = static_cast<const bf16*>(blk.w_fc2); f2.M = M; f2.N = D; f2.K = d->hidden;
+    f2.epi = emit ? (EPI_RESID | EPI_STATS) : EPI_RESID; f2.bias = blk.b_fc2; f2.residual = ws.x; f2.out = ws.x;
+    f2.stats_out = emit ? ws.parts : nullptr;
+    if ((rc = launch_gemm(f2, stream))) return rc;
+    *launches += 6;
+  }
+  return STAD_OK;
+}
+
+// Workspace of the whole MAE forward: encoder (B x n_vis tokens) | encoder_to_decoder output | decoder (B x N tokens).
+struct MaeWorkspace {
+  Workspace enc, dec;
+  bf16* vis;  // [B * n_vis, D_dec]
+  bf16* pix;  // [B * N, 1536]  pixel head over every row, before the masked rows are widened to fp32
+  size_t bytes;
+};
+
+MaeWorkspace carve_mae(const stad_mae_model* m, int B, int n_vis, int n_full, void* base) {
+  MaeWorkspace w;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  w.enc = carve(&m->encoder.dims, B, n_vis, p);
+  size_t off = w.enc.bytes;
+  w.vis = reinterpret_cast<bf16*>(p + off);
+  off += align256(static_cast<size_t>(B) * n_vis * m->dec_dims.dim * 2);
+  w.pix = reinterpret_cast<bf16*>(p + off);
+  off += align256(static_cast<size_t>(B) * n_full * m->dec_dims.num_classes * 2);
+  w.dec = carve(&m->dec_dims, B, n_full, p ? p + off : nullptr);
+  w.bytes = off + w.dec.bytes;
+  return w;
+}
+
+int full_tokens(const stad_dims* d) { return (d->frames / d->tubelet) * (d->img_h / 16) * (d->img_w / 16); }
+
 }  // namespace
 }  // namespace stad
 
@@ -324,36 +396,9 @@ int stad_vit_forward(const stad_model* m, const stad_input* in, const int32_t* t
   if ((rc = patch_embed_impl(in, m->w_patch, m->pos_bias, tok_idx, ws.x, ws.gather, d, B, n_tok, stream, &launches,
                              ws.parts, &parts)))
     return rc;
-  const int parts_resid = gemm_stat_parts(M, D, false, nullptr);
-
-  for (int l = 0; l < d->depth; ++l) {
-    const stad_block& blk = m->blocks[l];
-    const bool last = l + 1 == d->depth;
-    // x = x + proj(attn(norm1(x)))                                     (mf:161)
-    if ((rc = launch_stats_finalize(ws.parts, parts, ws.stats, M, D, m->eps, stream))) return rc;
-    GemmArgs q;
-    q.a = ws.x; q.w = static_cast<const bf16*>(blk.w_qkv); q.M = M; q.N = 3 * D; q.K = D;
-    q.epi = EPI_LN; q.bias = blk.b_qkv; q.colsum = blk.cs_qkv; q.stats = ws.stats; q.out = ws.qkv;
-    if ((rc = launch_gemm(q, stream))) return rc;
-    if ((rc = launch_attention(ws.qkv, ws.attn, B, d->heads, n_tok, m->attn_scale, stream))) return rc;
-    GemmArgs pr;
-    pr.a = ws.attn; pr.w = static_cast<const bf16*>(blk.w_proj); pr.M = M; pr.N = D; pr.K = D;
-    pr.epi = EPI_RESID | EPI_STATS; pr.bias = blk.b_proj; pr.residual = ws.x; pr.out = ws.x; pr.stats_out = ws.parts;
-    if ((rc = launch_gemm(pr, stream))) return rc;
-    parts = parts_resid;
-    // x = x + fc2(gelu(fc1(norm2(x))))                                 (mf:162)
-    if ((rc = launch_stats_finalize(ws.parts, parts, ws.stats, M, D, m->eps, stream))) return rc;
-    GemmArgs f1;
-    f1.a = ws.x; f1.w = static_cast<const bf16*>(blk.w_fc1); f1.M = M; f1.N = d->hidden; f1.K = D;
-    f1.epi = EPI_LN | EPI_GELU; f1.bias = blk.b_fc1; f1.colsum = blk.cs_fc1; f1.stats = ws.stats; f1.out = ws.hidden;
-    if ((rc = launch_gemm(f1, stream))) return rc;
-    GemmArgs f2;
-    f2.a = ws.hidden; f2.w = static_cast<const bf16*>(blk.w_fc2); f2.M = M; f2.N = D; f2.K = d->hidden;
-    f2.epi = last ? EPI_RESID : (EPI_RESID | EPI_STATS); f2.bias = blk.b_fc2; f2.residual = ws.x; f2.out = ws.x;
-    f2.stats_out = last ? nullptr : ws.parts;
-    if ((rc = launch_gemm(f2, stream))) return rc;
-    launches += 7;
-  }
+  if ((rc = run_blocks(m->blocks, d, m->eps, m->attn_scale, ws, B, n_tok, parts, /*final_stats=*/false, stream,
+                       &launches)))
+    return rc;
 
   if (classifier) {
     // norm = Identity; mean over tokens; fc_norm; head                (mf:323-326, mf:334)
@@ -366,6 +411,98 @@ int stad_vit_forward(const stad_model* m, const stad_input* in, const int32_t* t
     if ((rc = launch_layernorm(ws.x, m->norm_g, m->norm_b, tokens_out, M, D, m->eps, stream))) return rc;
     launches += 1;
   }
+  return launches;
+}
+
+int stad_decoder_assemble(const void* vis, const float* pos, const float* mask_token, const int32_t* mask_idx,
+                          void* x_full, float* stats, int B, int N, int n_vis, int D, float eps, stad_stream_t stream) {
+  STAD_CHECK_ARG(vis && pos && mask_token && mask_idx && x_full && stats, "decoder_assemble: NULL argument");
+  return launch_decoder_assemble(static_cast<const bf16*>(vis), pos, mask_token, mask_idx, static_cast<bf16*>(x_full),
+                                 reinterpret_cast<float2*>(stats), B, N, n_vis, D, eps, as_stream(stream));
+}
+
+int stad_tail_rows_f32(const void* x, float* y, int B, int N, int n_keep, int C, stad_stream_t stream) {
+  STAD_CHECK_ARG(x && y, "tail_rows: NULL argument");
+  return launch_tail_rows_f32(static_cast<const bf16*>(x), y, B, N, n_keep, C, as_stream(stream));
+}
+
+int stad_normalize_frames_u8(const void* frames_u8, void* out_bf16, int F, int H, int W, const float* mean,
+                             const float* std_, int bgr, stad_stream_t stream) {
+  STAD_CHECK_ARG(frames_u8 && out_bf16 && mean && std_, "normalize_frames_u8: NULL argument");
+  return launch_normalize_u8(static_cast<const uint8_t*>(frames_u8), static_cast<bf16*>(out_bf16), F, H, W, mean, std_,
+                             bgr, as_stream(stream));
+}
+
+size_t stad_mae_workspace_bytes(const stad_mae_model* m, int B, int n_vis) {
+  if (m == nullptr || B <= 0 || n_vis <= 0) return 0;
+  return carve_mae(m, B, n_vis, full_tokens(&m->encoder.dims), nullptr).bytes;
+}
+
+int stad_mae_forward(const stad_mae_model* m, const stad_input* in, const int32_t* vis_idx, const int32_t* mask_idx, int B,
+                     int n_vis, float* pixels, void* workspace, size_t workspace_bytes, stad_stream_t stream_) {
+  STAD_CHECK_ARG(m != nullptr && m->encoder.blocks != nullptr && m->dec_blocks != nullptr, "mae_forward: model is NULL");
+  STAD_CHECK_ARG(vis_idx != nullptr && mask_idx != nullptr && pixels != nullptr, "mae_forward: vis_idx / mask_idx / pixels is NULL");
+  const stad_dims* de = &m->encoder.dims;
+  const stad_dims* dd = &m->dec_dims;
+  int rc = check_dims(de);
+  if (rc) return rc;
+  const int N = full_tokens(de);
+  STAD_CHECK_ARG(B > 0 && n_vis > 0 && n_vis < N, "mae_forward: B=%d n_vis=%d (N=%d)", B, n_vis, N);
+  STAD_CHECK_ARG(de->heads * 64 == de->dim && dd->heads * 64 == dd->dim,
+                 "mae_forward: head dim must be 64 (encoder %d/%d, decoder %d/%d)", de->dim, de->heads, dd->dim, dd->heads);
+  STAD_CHECK_ARG(dd->dim % 64 == 0 && dd->num_classes > 0 && dd->num_classes % 64 == 0,
+                 "mae_forward: decoder dim=%d classes=%d", dd->dim, dd->num_classes);
+  STAD_CHECK_ARG(m->w_e2d && m->b_e2d && m->cs_e2d && m->pos_dec && m->mask_token && m->w_pix && m->b_pix && m->cs_pix,
+                 "mae_forward: decoder weights missing");
+  STAD_CHECK_ARG(workspace != nullptr, "mae_forward: workspace is NULL");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(STAD_E_ALIGN, "mae_forward: workspace must be 256-byte aligned");
+  MaeWorkspace ws = carve_mae(m, B, n_vis, N, workspace);
+  STAD_CHECK_ARG(ws.bytes <= workspace_bytes, "mae_forward: workspace too small (%zu < %zu bytes)", workspace_bytes,
+                 ws.bytes);
+  cudaStream_t stream = as_stream(stream_);
+  const float eps = m->encoder.eps, scale = m->encoder.attn_scale;
+  int launches = 0;
+
+  // ---- encoder over the visible tokens (mp:91-106)
+  int parts = 0;
+  if ((rc = patch_embed_impl(in, m->encoder.w_patch, m->encoder.pos_bias, vis_idx, ws.enc.x, ws.enc.gather, de, B, n_vis,
+                             stream, &launches, ws.enc.parts, &parts)))
+    return rc;
+  if ((rc = run_blocks(m->encoder.blocks, de, eps, scale, ws.enc, B, n_vis, parts, /*final_stats=*/true, stream,
+                       &launches)))
+    return rc;
+  // ---- x_vis = encoder_to_decoder(norm(x)) + pos_emd_vis              (mp:107, mp:281, mp:287)
+  const int Mv = B * n_vis;
+  if ((rc = launch_stats_finalize(ws.enc.parts, gemm_stat_parts(Mv, de->dim, false, nullptr), ws.enc.stats, Mv, de->dim,
+                                  eps, stream)))
+    return rc;
+  GemmArgs e;
+  e.a = ws.enc.x; e.w = static_cast<const bf16*>(m->w_e2d); e.M = Mv; e.N = dd->dim; e.K = de->dim;
+  e.epi = EPI_LN | EPI_POS; e.bias = m->b_e2d; e.colsum = m->cs_e2d; e.stats = ws.enc.stats; e.out = ws.vis;
+  e.pos = m->pos_dec; e.tok_idx = vis_idx; e.pos_rows = N;
+  if ((rc = launch_gemm(e, stream))) return rc;
+  // ---- x_full = cat(x_vis, mask_token + pos_emd_mask) + statistics     (mp:283-288)
+  if ((rc = launch_decoder_assemble(ws.vis, m->pos_dec, m->mask_token, mask_idx, ws.dec.x, ws.dec.stats, B, N, n_vis,
+                                    dd->dim, eps, stream)))
+    return rc;
+  launches += 3;
+  // ---- decoder blocks over all N tokens                                 (mp:165-171)
+  if ((rc = run_blocks(m->dec_blocks, dd, eps, scale, ws.dec, B, N, 0, /*final_stats=*/true, stream, &launches)))
+    return rc;
+  // ---- head(norm(x[:, -n_mask:]))                                       (mp:173-174)
+  // The LayerNorm-folded head runs over every row (the visible rows, 10 % at mask ratio 0.9, are computed and dropped:
+  // rows of one clip are contiguous, the masked rows of the batch are not); the masked rows of its bf16 result are
+  // then widened to fp32 into `pixels`.
+  const int Mf = B * N;
+  if ((rc = launch_stats_finalize(ws.dec.parts, gemm_stat_parts(Mf, dd->dim, false, nullptr), ws.dec.stats, Mf, dd->dim,
+                                  eps, stream)))
+    return rc;
+  GemmArgs h;
+  h.a = ws.dec.x; h.w = static_cast<const bf16*>(m->w_pix); h.M = Mf; h.N = dd->num_classes; h.K = dd->dim;
+  h.epi = EPI_LN; h.bias = m->b_pix; h.colsum = m->cs_pix; h.stats = ws.dec.stats; h.out = ws.pix;
+  if ((rc = launch_gemm(h, stream))) return rc;
+  if ((rc = launch_tail_rows_f32(ws.pix, pixels, B, N, N - n_vis, dd->num_classes, stream))) return rc;
+  launches += 3;
   return launches;
 }
 

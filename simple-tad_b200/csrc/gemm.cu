@@ -491,6 +491,7 @@ int gemm_init() {
   if ((rc = set_smem_all_bn<EPI_RESID | EPI_STATS, false>())) return rc;
   if ((rc = set_smem_all_bn<EPI_POS | EPI_STATS, false>())) return rc;
   if ((rc = set_smem_all_bn<EPI_POS | EPI_STATS, true>())) return rc;
+  if ((rc = set_smem_all_bn<EPI_LN | EPI_POS, false>())) return rc;
   return STAD_OK;
 }
 
@@ -584,6 +585,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     case EPI_LN | EPI_GELU: return dispatch_bn<EPI_LN | EPI_GELU, false>(bn, ta, tb, to, tr, ka, stream);
     case EPI_RESID: return dispatch_bn<EPI_RESID, false>(bn, ta, tb, to, tr, ka, stream);
     case EPI_POS: return dispatch_bn<EPI_POS, false>(bn, ta, tb, to, tr, ka, stream);
+    case EPI_LN | EPI_POS: return dispatch_bn<EPI_LN | EPI_POS, false>(bn, ta, tb, to, tr, ka, stream);
   }
   return fail(STAD_E_SHAPE, "gemm: unsupported epilogue combination %d", g.epi);
 }

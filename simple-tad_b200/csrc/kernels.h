@@ -59,4 +59,11 @@ int launch_pool_norm_head(const bf16* x, const float* g, const float* b, const f
 int launch_gather_patches(const bf16* planes, const PatchGeom& pg, const int32_t* tok_idx, bf16* out, int B,
                           int n_tok, cudaStream_t stream);
 
+// MAE decoder glue (modeling_pretrain.py:283-288, :174) and uint8 frame preparation (run_inference.py:15-34)
+int launch_decoder_assemble(const bf16* vis, const float* pos, const float* mask_token, const int32_t* mask_idx, bf16* x,
+                            float2* stats, int B, int N, int n_vis, int D, float eps, cudaStream_t stream);
+int launch_tail_rows_f32(const bf16* x, float* y, int B, int N, int n_keep, int C, cudaStream_t stream);
+int launch_normalize_u8(const uint8_t* in, bf16* out, int F, int H, int W, const float* mean, const float* std_, int bgr,
+                        cudaStream_t stream);
+
 }  // namespace stad

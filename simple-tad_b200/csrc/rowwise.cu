@@ -261,6 +261,126 @@ gather_patches_kernel(const bf16* __restrict__ planes, PatchGeom pg, const int32
   reinterpret_cast<uint4*>(out)[i] = __ldg(reinterpret_cast<const uint4*>(planes + src));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// MAE decoder input (modeling_pretrain.py:283-288): x_full[b] = cat(x_vis[b] (+ pos, already added by the
+// encoder_to_decoder GEMM epilogue), mask_token + pos[masked ids of clip b]) and, in the same pass, the LayerNorm
+// statistics of every row of x_full for the first decoder block's norm1.  One warp per output row.
+// Bytes: 2 B n_vis D read + 2 B N D written (+ 8 B N); the position table [N, D] fp32 stays in L2.
+__global__ void __launch_bounds__(256)
+decoder_assemble_kernel(const bf16* __restrict__ vis, const float* __restrict__ pos,
+                        const float* __restrict__ mask_token, const int32_t* __restrict__ mask_idx,
+                        bf16* __restrict__ x, float2* __restrict__ stats, int B, int N, int n_vis, int D, float eps) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B * N) return;
+  const int b = row / N;
+  const int i = row - b * N;
+  const int chunks = D >> 3;
+  uint4* xr = reinterpret_cast<uint4*>(x + static_cast<size_t>(row) * D);
+  float v[kMaxChunks][8];
+  float s = 0.f;
+  const bool visible = i < n_vis;
+  const uint4* vr = reinterpret_cast<const uint4*>(vis + (static_cast<size_t>(b) * n_vis + (visible ? i : 0)) * D);
+  const float* pr =
+      pos + static_cast<size_t>(visible ? 0 : __ldg(&mask_idx[static_cast<size_t>(b) * (N - n_vis) + (i - n_vis)])) * D;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int idx = c * 32 + lane;
+    if (idx < chunks) {
+      uint4 u;
+      if (visible) {
+        u = __ldg(vr + idx);
+      } else {
+        const int col = idx * 8;
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(pr + col));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(pr + col + 4));
+        const float4 m0 = __ldg(reinterpret_cast<const float4*>(mask_token + col));
+        const float4 m1 = __ldg(reinterpret_cast<const float4*>(mask_token + col + 4));
+        u.x = pack_bf16(m0.x + p0.x, m0.y + p0.y);
+        u.y = pack_bf16(m0.z + p0.z, m0.w + p0.w);
+        u.z = pack_bf16(m1.x + p1.x, m1.y + p1.y);
+        u.w = pack_bf16(m1.z + p1.z, m1.w + p1.w);
+      }
+      xr[idx] = u;
+      unpack8(u, v[c]);  // statistics of the values as stored (bf16)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[c][j];
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int idx = c * 32 + lane;
+    if (idx < chunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[c][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float var = warp_sum(q) / static_cast<float>(D);
+  if (lane == 0) stats[row] = make_float2(mean, rsqrtf(var + eps));
+}
+
+// Last n_keep rows of every clip of x[B, N, C] bf16 -> y[B, n_keep, C] fp32 (the decoder returns only the predictions
+// of the masked tokens, modeling_pretrain.py:174).  Bytes: 2 B n_keep C read + 4 B n_keep C written.
+__global__ void __launch_bounds__(256)
+tail_rows_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, int N, int n_keep, int c8, size_t total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = static_cast<int>(i % c8);
+  const size_t r = i / c8;
+  const size_t b = r / n_keep;
+  const int j = static_cast<int>(r - b * n_keep);
+  const size_t src = (b * N + (N - n_keep) + j) * static_cast<size_t>(c8) + ch;
+  float f[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(x) + src), f);
+  float4* o = reinterpret_cast<float4*>(y) + 2 * i;
+  o[0] = make_float4(f[0], f[1], f[2], f[3]);
+  o[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Frame preparation (run_inference.py:15-34 prepare_image; dota.py:347-348 + volume_transforms ClipToTensor/normalize):
+// uint8 HWC frames (BGR as cv2.imread returns them, or RGB) -> bf16 planes [F, 3, H, W] = (v / 255 - mean[c]) / std[c]
+// with c the RGB channel.  One thread converts 8 consecutive pixels of one row (24 input bytes, three 16-byte stores).
+// Bytes: 3 F H W read + 6 F H W written.
+struct NormArgs {
+  float scale[3];  // 1 / (255 std[c])
+  float shift[3];  // -mean[c] / std[c]
+};
+__global__ void __launch_bounds__(256)
+normalize_u8_kernel(const uint8_t* __restrict__ in, bf16* __restrict__ out, int HW, int hw8, size_t total, NormArgs na,
+                    int bgr) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t f = i / hw8;
+  const int p8 = static_cast<int>(i - f * hw8);
+  // 24 bytes = 8 pixels x 3 interleaved channels; 8-byte aligned because HW % 8 == 0
+  const uint2* src = reinterpret_cast<const uint2*>(in + (f * HW + static_cast<size_t>(p8) * 8) * 3);
+  const uint2 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+  const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+  float px[3][8];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) {
+    const float val = static_cast<float>((w[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+    px[k % 3][k / 3] = val;
+  }
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const int srcc = bgr ? 2 - ch : ch;  // output plane ch (R, G, B) reads interleaved channel srcc
+    uint4 o;
+    const float sc = na.scale[ch], sh = na.shift[ch];
+    o.x = pack_bf16(fmaf(px[srcc][0], sc, sh), fmaf(px[srcc][1], sc, sh));
+    o.y = pack_bf16(fmaf(px[srcc][2], sc, sh), fmaf(px[srcc][3], sc, sh));
+    o.z = pack_bf16(fmaf(px[srcc][4], sc, sh), fmaf(px[srcc][5], sc, sh));
+    o.w = pack_bf16(fmaf(px[srcc][6], sc, sh), fmaf(px[srcc][7], sc, sh));
+    reinterpret_cast<uint4*>(out + (f * 3 + ch) * HW)[p8] = o;
+  }
+}
+
 }  // namespace
 
 int launch_cast_f32_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream) {
@@ -353,6 +473,57 @@ int launch_gather_patches(const bf16* planes, const PatchGeom& pg, const int32_t
   gather_patches_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
       planes, pg, tok_idx, out, B, n_tok, K);
   STAD_LAUNCH_OK("gather_patches");
+  return STAD_OK;
+}
+
+int launch_decoder_assemble(const bf16* vis, const float* pos, const float* mask_token, const int32_t* mask_idx, bf16* x,
+                            float2* stats, int B, int N, int n_vis, int D, float eps, cudaStream_t stream) {
+  int rc = check_row_args(x, B * N, D);
+  if (rc) return rc;
+  STAD_CHECK_ARG(n_vis > 0 && n_vis < N, "decoder_assemble: n_vis=%d must be in (0, %d)", n_vis, N);
+  if ((reinterpret_cast<uintptr_t>(vis) | reinterpret_cast<uintptr_t>(pos) | reinterpret_cast<uintptr_t>(mask_token)) & 15)
+    return fail(STAD_E_ALIGN, "decoder_assemble: vis, pos, mask_token must be 16-byte aligned");
+  const int rows_per_block = 8;
+  ProfScope prof(STAD_K_ASSEMBLE, 0, B * N, D, n_vis, stream);
+  decoder_assemble_kernel<<<ceil_div(B * N, rows_per_block), rows_per_block * 32, 0, stream>>>(
+      vis, pos, mask_token, mask_idx, x, stats, B, N, n_vis, D, eps);
+  STAD_LAUNCH_OK("decoder_assemble");
+  return STAD_OK;
+}
+
+int launch_tail_rows_f32(const bf16* x, float* y, int B, int N, int n_keep, int C, cudaStream_t stream) {
+  STAD_CHECK_ARG(B > 0 && n_keep > 0 && n_keep <= N && C > 0 && C % 8 == 0, "tail_rows: B=%d N=%d n_keep=%d C=%d", B, N,
+                 n_keep, C);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15)
+    return fail(STAD_E_ALIGN, "tail_rows: pointers must be 16-byte aligned");
+  const size_t total = static_cast<size_t>(B) * n_keep * (C >> 3);
+  const int threads = 256;
+  ProfScope prof(STAD_K_TAIL, 0, B * n_keep, C, 0, stream);
+  tail_rows_f32_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(x, y, N, n_keep,
+                                                                                                      C >> 3, total);
+  STAD_LAUNCH_OK("tail_rows_f32");
+  return STAD_OK;
+}
+
+int launch_normalize_u8(const uint8_t* in, bf16* out, int F, int H, int W, const float* mean, const float* std_, int bgr,
+                        cudaStream_t stream) {
+  STAD_CHECK_ARG(F > 0 && H > 0 && W > 0 && (static_cast<long long>(H) * W) % 8 == 0,
+                 "normalize_u8: F=%d H=%d W=%d (H*W must be a multiple of 8)", F, H, W);
+  if ((reinterpret_cast<uintptr_t>(in) & 7) | (reinterpret_cast<uintptr_t>(out) & 15))
+    return fail(STAD_E_ALIGN, "normalize_u8: in must be 8-byte and out 16-byte aligned");
+  NormArgs na;
+  for (int c = 0; c < 3; ++c) {
+    STAD_CHECK_ARG(std_[c] > 0.f, "normalize_u8: std[%d] must be positive", c);
+    na.scale[c] = 1.0f / (255.0f * std_[c]);
+    na.shift[c] = -mean[c] / std_[c];
+  }
+  const int HW = H * W;
+  const size_t total = static_cast<size_t>(F) * (HW >> 3);
+  const int threads = 256;
+  ProfScope prof(STAD_K_NORMALIZE, 0, F, HW, 0, stream);
+  normalize_u8_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
+      in, out, HW, HW >> 3, total, na, bgr);
+  STAD_LAUNCH_OK("normalize_u8");
   return STAD_OK;
 }
 

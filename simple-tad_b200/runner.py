@@ -14,6 +14,11 @@ import math
 import torch
 import torch.distributed as dist
 
+from . import _lib
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)  # model.default_cfg mean / std, ri:56-62
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
 
 def shard_range(n, world_size, rank):
     """Contiguous block of window indices owned by `rank`: (lo, hi, per_rank) with per_rank = ceil(n / world)."""
@@ -62,6 +67,7 @@ class SlidingWindowRunner:
         self.stride = int(stride)
         self.T = model.num_frames
         self._dev_frames = None
+        self._norm_frames = None
 
     def _upload(self, frames):
         """Host frames [F, C, H, W] -> reused device buffer (async copy on the current stream if pinned)."""
@@ -95,6 +101,23 @@ class SlidingWindowRunner:
         """As above, returning host tensors: the per-frame anomaly probabilities a caller prints (ri:104-108).
         Window w's score belongs to frame w + T - 1 (label = last frame, dota.py:217-223)."""
         logits, probs = self.score_frames_device(frames)
+        return logits.cpu(), probs.cpu()
+
+    @torch.no_grad()
+    def score_frames_u8(self, frames_u8, bgr=True, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+        """uint8 frames [F, H, W, 3] exactly as cv2 hands them over after the resize (BGR when bgr=True, ri:79-81)
+        -> host (logits, probs).  The H2D copy moves 1 byte per value (the fp32 path of the reference moves 4, ri:82)
+        and prepare_image's cvtColor / div 255 / normalise / HWC->CHW (ri:15-34) run in one kernel on the device
+        (stad_normalize_frames_u8) straight into the bf16 frame buffer the patch-embed kernel reads."""
+        if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3:
+            raise ValueError(f"expected uint8 frames [F, H, W, 3], got {frames_u8.dtype} {tuple(frames_u8.shape)}")
+        dev = self._upload(frames_u8.contiguous())
+        n = dev.numel()
+        if self._norm_frames is None or self._norm_frames.numel() < n:
+            self._norm_frames = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+        F_, H, W, _ = dev.shape
+        planes = _lib.normalize_frames_u8(dev, mean, std, bgr=bgr, out=self._norm_frames[:n].view(F_, 3, H, W))
+        logits, probs = self.score_frames_device(planes)
         return logits.cpu(), probs.cpu()
 
     @torch.no_grad()

@@ -68,3 +68,17 @@ def build_encoder(arch, sd, device="cuda"):
                                                 norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), init_values=0.)
     model.load_state_dict(sd, strict=True)
     return model.to(device).eval()
+
+
+def build_pretrain(arch, sd, decoder_depth, device="cuda"):
+    """The full PretrainVisionTransformer drop-in (encoder + decoder) with a reference-format state dict loaded."""
+    from simple_tad_b200 import modeling_pretrain as mp
+    from functools import partial
+    D, depth, heads = synth.ARCHS[arch]
+    Dd, dheads = synth.DECODERS[arch]
+    model = mp.PretrainVisionTransformer(
+        img_size=224, patch_size=16, encoder_embed_dim=D, encoder_depth=depth, encoder_num_heads=heads,
+        encoder_num_classes=0, decoder_num_classes=1536, decoder_embed_dim=Dd, decoder_num_heads=dheads,
+        decoder_depth=decoder_depth, mlp_ratio=4, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    model.load_state_dict(sd, strict=True)
+    return model.to(device).eval()

@@ -48,9 +48,21 @@ def test_state_dict_contract_matches_reference_names_and_shapes():
         for k in sd:
             assert own[k].shape == sd[k].shape, k
         assert "blocks.0.attn.qkv.bias" not in own and "blocks.0.attn.q_bias" in own  # K has no bias (mf:69-75)
-    enc = mp.pretrain_videomae_base_patch16_224(decoder_depth=4)
+    full = mp.pretrain_videomae_base_patch16_224(decoder_depth=4)
     sde = synth.make_state_dict("vit_base_patch16_224", encoder=True)
-    assert set(enc.state_dict()) == set(sde) and "norm.weight" in sde and "head.weight" not in sde
+    assert set(full.encoder.state_dict()) == set(sde) and "norm.weight" in sde and "head.weight" not in sde
+    # full pre-training model (mp:183-258): encoder.*, decoder.*, encoder_to_decoder.weight (no bias), mask_token
+    sdp = synth.make_pretrain_state_dict("vit_base_patch16_224", decoder_depth=4)
+    own = full.state_dict()
+    assert set(own) == set(sdp)
+    for k in sdp:
+        assert own[k].shape == sdp[k].shape, k
+    assert "pos_embed" not in own and full.pos_embed.shape == (1, 1568, 384)
+    assert own["decoder.head.weight"].shape == (1536, 384) and own["mask_token"].shape == (1, 1, 384)
+    assert sum(p.numel() for p in full.parameters()) == 94_210_944  # VideoMAE-B pre-training model, decoder depth 4
+    assert full.no_weight_decay() == {"pos_embed", "cls_token", "mask_token"}
+    small = mp.pretrain_videomae_small_patch16_224(decoder_depth=4)
+    assert small.decoder.embed_dim == 192 and small.decoder.num_heads == 3
 
 
 def test_sinusoid_table_is_bit_identical_to_the_oracle():
@@ -99,6 +111,35 @@ def test_visible_token_indices_match_boolean_indexing_order():
     assert torch.equal(idx, vit_oracle.visible_indices(mask))
     idx75, n75 = mp.visible_token_indices(synth.tube_mask(2, 0.75, seed=1))
     assert n75 == 392
+
+
+def test_masked_token_indices_complement_the_visible_ones():
+    mask = synth.tube_mask(3, 0.9, seed=5)
+    vis, nv = mp.visible_token_indices(mask)
+    msk, nm = mp.masked_token_indices(mask)
+    assert nv == 160 and nm == 1408 and msk.dtype == torch.int32
+    for b in range(3):
+        assert torch.equal(msk[b].long(), mask[b].nonzero().flatten())          # row-major order of x[mask] (mp:286)
+        assert sorted(vis[b].tolist() + msk[b].tolist()) == list(range(1568))
+
+
+def test_norm_fold_of_the_pixel_head_is_exact():
+    """decoder.norm folded into decoder.head (and encoder.norm into encoder_to_decoder, which has no bias)."""
+    torch.manual_seed(1)
+    norm = torch.nn.LayerNorm(192, eps=1e-6)
+    lin = torch.nn.Linear(192, 1536)
+    e2d = torch.nn.Linear(192, 128, bias=False)
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.1 * torch.randn(192))
+        norm.bias.copy_(0.05 * torch.randn(192))
+    x = torch.randn(40, 192) * 1.5 + 0.3
+    mean = x.mean(1, keepdim=True)
+    rstd = (x.var(1, unbiased=False, keepdim=True) + 1e-6).rsqrt()
+    for layer in (lin, e2d):
+        w, b, cs = mp._fold_norm_linear(norm, layer.weight, layer.bias, "cpu")
+        ref = layer(norm(x))
+        got = rstd * (x @ w.float().t() - mean * cs) + b
+        assert float((got - ref).abs().max()) < 2e-2 * float(ref.abs().max())
 
 
 def test_inference_only_and_cuda_only():

@@ -112,6 +112,119 @@ def test_config4_masked_encoder():
     assert cos_b >= parity.TOL_COS, f"config4 @B=100: worst token cosine {cos_b:.6f}"
 
 
+def _check_pixels(y, g, what):
+    from oracle.make_golden import PIX_TOK_STEP, PIX_VAL_STEP
+    y = y.float().cpu()
+    assert torch.isfinite(y).all(), f"{what}: non-finite pixels"
+    ref = torch.from_numpy(g["pixels_sample"])
+    got = y[:, ::PIX_TOK_STEP, ::PIX_VAL_STEP]
+    rel = float((got - ref).norm() / ref.norm())
+    cos = parity.row_cosine_min(got, ref)
+    assert rel <= parity.TOL_HIDDEN_REL_L2, f"{what}: sampled pixels rel-L2 {rel:.3e}"
+    assert cos >= parity.TOL_COS, f"{what}: worst sampled-token cosine {cos:.6f}"
+    nrm = torch.from_numpy(g["pixel_norm"])
+    rel_n = float(((y.norm(dim=-1) - nrm).abs() / nrm).max())
+    assert rel_n <= 3e-2, f"{what}: worst per-token norm error {rel_n:.3e}"     # EVERY predicted token
+    return rel, cos
+
+
+def test_mae_small_vs_reference_and_oracle():
+    """Full PretrainVisionTransformer (encoder -> encoder_to_decoder -> mask tokens -> decoder -> pixel head, mp:276-291),
+    ViT-S width (decoder 192 / 3 heads, depth 2): one stad_mae_forward call vs the unmodified reference's output, the live
+    oracle on every pixel, and the module-level decoder against the oracle's decoder."""
+    g = parity.golden("small_mae_vits_d2_b2")
+    arch = "vit_small_d2"
+    D, depth, heads = synth.ARCHS[arch]
+    Dd, dheads = synth.DECODERS[arch]
+    sd = synth.make_pretrain_state_dict(arch, seed=14, decoder_depth=2)
+    model = parity.build_pretrain(arch, sd, decoder_depth=2)
+    x = synth.make_clips(2, seed=14)
+    mask = synth.tube_mask(2, 0.9, seed=14)
+    y = model(x.to(DEV), mask.to(DEV))
+    assert y.shape == (2, 1408, 1536) and y.dtype == torch.float32
+    _check_pixels(y, g, "mae small")
+    ref = vit_oracle.pretrain_forward(sd, x, mask, heads, dheads)
+    rel = float((y.cpu() - ref).norm() / ref.norm())
+    assert rel <= parity.TOL_HIDDEN_REL_L2, f"mae small vs live oracle: rel-L2 {rel:.3e}"
+    assert parity.row_cosine_min(y.cpu(), ref) >= parity.TOL_COS
+    # other mask ratio (0.75 -> 392 visible): ragged M tiles in the encoder, different split in the decoder
+    mask75 = synth.tube_mask(2, 0.75, seed=15)
+    y75 = model(x.to(DEV), mask75.to(DEV))
+    ref75 = vit_oracle.pretrain_forward(sd, x, mask75, heads, dheads)
+    assert y75.shape == (2, 1176, 1536)
+    assert float((y75.cpu() - ref75).norm() / ref75.norm()) <= parity.TOL_HIDDEN_REL_L2
+    # module-level decoder (stand-alone use of PretrainVisionTransformerDecoder.forward, mp:164-178)
+    gen = torch.Generator().manual_seed(9)
+    xd = synth.bf16_round(torch.randn(2, 392, Dd, generator=gen))
+    dsd = {k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}
+    for rtn in (300, 0):
+        yd = model.decoder(xd.to(DEV), rtn)
+        refd = vit_oracle.decoder_forward(dsd, xd, rtn, dheads)
+        assert yd.shape == refd.shape
+        assert float((yd.cpu() - refd).norm() / refd.norm()) <= parity.TOL_HIDDEN_REL_L2
+
+
+def test_config4_mae_vitb_full_pretrain_forward():
+    """BASELINE config 4 widened to the full DAPT forward: VideoMAE-B pre-training model, decoder depth 4,
+    90 % tube masking, vs the unmodified reference; batch invariance at a larger batch."""
+    g = parity.golden("c4_mae_vitb_b2")
+    arch = "vit_base_patch16_224"
+    sd = synth.make_pretrain_state_dict(arch, seed=6, decoder_depth=4)
+    model = parity.build_pretrain(arch, sd, decoder_depth=4)
+    x = synth.make_clips(2, seed=6)
+    mask = synth.tube_mask(2, 0.9, seed=6)
+    assert (mask.numpy() == g["mask"]).all()
+    y = model(x.to(DEV), mask.to(DEV))
+    assert y.shape == (2, 1408, 1536)
+    _check_pixels(y, g, "config4 mae ViT-B")
+    xb = torch.cat([x, synth.make_clips(10, seed=60)]).to(DEV)
+    mb = torch.cat([mask, synth.tube_mask(10, 0.9, seed=60)]).to(DEV)
+    yb = model(xb, mb)
+    assert yb.shape == (12, 1408, 1536) and torch.isfinite(yb).all()
+    _check_pixels(yb[:2], g, "config4 mae ViT-B @B=12")
+    assert model.prepare().last_launches == 2 + 12 * 7 + 3 + 4 * 7 - 1 + 3
+
+
+def test_frames_from_uint8_match_the_fp32_path():
+    """uint8 frames -> stad_normalize_frames_u8 -> forward_windows equals the reference's prepare_image arithmetic
+    (ri:15-34) followed by the same windows, within the parity tolerance; runner end to end from uint8."""
+    from simple_tad_b200.runner import SlidingWindowRunner
+    sd = synth.make_state_dict("vit_small_d2", seed=11)
+    model = parity.build_classifier("vit_small_d2", sd)
+    g = torch.Generator().manual_seed(77)
+    u8 = torch.randint(0, 256, (20, 224, 224, 3), generator=g, dtype=torch.uint8)       # BGR HWC, as cv2.imread
+    img = u8.flip(-1).permute(0, 3, 1, 2).float().div_(255.0)
+    mean = torch.tensor(synth.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(synth.IMAGENET_STD).view(1, 3, 1, 1)
+    frames = (img - mean) / std
+    ref_logits, _ = model.forward_windows(frames.to(DEV))
+    runner = SlidingWindowRunner(model, batch_windows=4)
+    logits, probs = runner.score_frames_u8(u8, bgr=True)
+    assert logits.shape == (5, 2)
+    parity.check_logits(logits, ref_logits, "uint8 frames vs fp32 frames")
+    clips = synth.windows_from_video(synth.bf16_round(frames))
+    parity.check_logits(logits, vit_oracle.vit_forward(sd, clips, 6), "uint8 frames vs oracle")
+
+
+def test_efficiency_harness_and_cuda_graph_replay():
+    """test_efficiency.py shape (te:12-196, config 5): the forward replayed from a CUDA graph returns bit-identical
+    logits to the eager call, for new inputs too; main() / batch_sweep() report sane numbers."""
+    from simple_tad_b200 import efficiency
+    sd = synth.make_state_dict("vit_small_d2", seed=11)
+    model = parity.build_classifier("vit_small_d2", sd)
+    x = synth.make_clips(2, seed=31).to(DEV)
+    eager = model(x).clone()
+    fwd = efficiency.GraphedForward(model, x)
+    assert torch.equal(fwd.run(), eager)
+    x2 = synth.make_clips(2, seed=32).to(DEV)
+    assert torch.equal(fwd.run(x2).clone(), model(x2))
+    assert torch.equal(fwd.run(x), eager)
+    res = efficiency.main("VideoMAE-S", with_flash=True, steps=5, quiet=True)
+    assert res["params"] == 21_880_706 and res["avg_ms"] > 0 and res["fps"] > 0
+    rows = efficiency.batch_sweep("VideoMAE-S", batches=(1, 3), warmup=2, iters=3, quiet=True)
+    assert [r["batch_per_gpu"] for r in rows] == [1, 3] and all(r["clips_per_s"] > 0 for r in rows)
+
+
 def test_config5_batch_sweep_consistency():
     """BASELINE config 5 (correctness side of the batch sweep): ViT-B logits for the same clips at batch 1, 2, 8
     all match the reference within tolerance."""

@@ -81,6 +81,46 @@ def test_config4_encoder_one_clip():
     np.testing.assert_allclose(y.norm(dim=-1).numpy(), g["token_norm"][:1], rtol=1e-4)
 
 
+def test_small_pretrain_model_pixels():
+    """Full PretrainVisionTransformer (encoder -> encoder_to_decoder -> mask tokens + pos -> decoder -> pixel head on
+    the masked tokens, mp:276-291) against the unmodified reference's output."""
+    from oracle.make_golden import PIX_TOK_STEP, PIX_VAL_STEP
+    g = parity.golden("small_mae_vits_d2_b2")
+    arch = "vit_small_d2"
+    D, depth, heads = synth.ARCHS[arch]
+    Dd, dheads = synth.DECODERS[arch]
+    sd = synth.make_pretrain_state_dict(arch, seed=14, decoder_depth=2)
+    x = synth.make_clips(2, seed=14)
+    mask = synth.tube_mask(2, 0.9, seed=14)
+    assert (mask.numpy() == g["mask"]).all()
+    y = vit_oracle.pretrain_forward(sd, x, mask, heads, dheads)
+    assert y.shape == (2, 1408, 1536)
+    np.testing.assert_allclose(y[:, ::PIX_TOK_STEP, ::PIX_VAL_STEP].numpy(), g["pixels_sample"], atol=ATOL)
+    np.testing.assert_allclose(y.norm(dim=-1).numpy(), g["pixel_norm"], rtol=1e-4)
+    np.testing.assert_allclose(y.mean(dim=1).numpy(), g["pixel_mean"], atol=ATOL)
+    assert float(y.std()) > 0.1  # informative fixture
+
+
+def test_tube_masking_generator_matches_reference_draws():
+    """oracle and product TubeMaskingGenerator vs the reference's draws under the same np.random seed
+    (masking_generator.py:3-23; fixture written by oracle/make_golden.gen_masks)."""
+    from simple_tad_b200.masking_generator import TubeMaskingGenerator, batch_masks
+    g = parity.golden("tube_masks")
+    for seed in (0, 1, 2):
+        ratio = float(g[f"ratio_s{seed}"])
+        for cls in (vit_oracle.TubeMaskingGenerator, TubeMaskingGenerator):
+            np.random.seed(seed)
+            gen = cls((8, 14, 14), ratio)
+            got = np.stack([gen() for _ in range(3)])
+            assert got.dtype == np.float64 and got.shape == (3, 1568)
+            np.testing.assert_array_equal(got, g[f"mask_s{seed}"])
+        np.random.seed(seed)
+        m = batch_masks(TubeMaskingGenerator((8, 14, 14), ratio), 3)
+        assert m.dtype == torch.bool and np.array_equal(m.numpy(), g[f"mask_s{seed}"].astype(bool))
+    gen = TubeMaskingGenerator((8, 14, 14), 0.9)
+    assert gen.total_masks == 8 * 176 and gen.num_visible == 160 and "mask patches 1408" in repr(gen)
+
+
 def test_sinusoid_table_matches_reference_formula():
     """mf:195-205 evaluated literally (python loops) on a small table."""
     n, d = 7, 10
