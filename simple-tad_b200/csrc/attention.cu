@@ -83,7 +83,7 @@ struct AttArgs {
 #define STAD_ATT_PIPE 0
 #endif
 #ifndef STAD_ATT_STAGGER
-#define STAD_ATT_STAGGER 0
+#define STAD_ATT_STAGGER 2
 #endif
 #ifndef STAD_ATT_PROBE
 #define STAD_ATT_PROBE 1
@@ -250,7 +250,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
         }
         const bool solo = w.slots == 1;
         // S = Q K^T over the first `cols` keys of K tile number kc (its k_full wait has been done); releases the stage
-        auto issue_qk = [&](int cols, bool last_of_unit) {
+        // (`solo_unit`: the unit the tile belongs to has one slot, so this warp releases the stage for both)
+        auto issue_qk = [&](int cols, bool last_of_unit, bool solo_unit) {
           const uint32_t kst = kc % K_STAGES;
           tc_fence_after();
           ATT_EV(2 + slot, 20);
@@ -268,7 +269,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
             umma_commit(&s_full[slot]);
             if (last_of_unit) umma_commit(&q_free[slot]);
             umma_commit(&k_free[kst]);
-            if (solo) umma_commit(&k_free[kst]);
+            if (solo_unit) umma_commit(&k_free[kst]);
           }
           __syncwarp();
           ++kc;
@@ -303,7 +304,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
         mbar_wait(&q_full[slot], ucnt & 1);
         wait_k();
         if (g > 0) mbar_wait(&s_free[slot], (g - 1) & 1);  // previous S of the slot has been pulled out of TMEM
-        issue_qk(n_kv == 1 ? last_chunks * 32 : BKV, n_kv == 1);
+        issue_qk(n_kv == 1 ? last_chunks * 32 : BKV, n_kv == 1, solo);
         for (int j = 0; j < n_kv; ++j) {
           const bool has_next = j + 1 < n_kv;
           const bool next_last = j + 2 == n_kv;
@@ -314,7 +315,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
             ATT_EV(2 + slot, 10);
             mbar_wait(&s_free[slot], (g + j) & 1);
             ATT_EV(2 + slot, 11);
-            issue_qk(next_last ? last_chunks * 32 : BKV, next_last);
+            issue_qk(next_last ? last_chunks * 32 : BKV, next_last, solo);
             ATT_EV(2 + slot, 12);
           }
           wait_v();
@@ -422,9 +423,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
       for (int j = 0; j < n_kv; ++j, ++g) {
         ATT_T(7);
 #if STAD_ATT_STAGGER
-        // One-time phase offset between the two slots: without it both softmax warpgroups run in lockstep (same
-        // phase of the iteration at the same time), i.e. they fight for the MUFU together and idle together.
-        if (g == 0) {
+        const bool kStaggerNow = STAD_ATT_STAGGER == 2 ? (j == 0 && w.slots == 2) : (g == 0);
+        // Phase offset between the two slots: without it both softmax warpgroups run in lockstep (same phase of the
+        // iteration at the same time), i.e. they fight for the MUFU together and idle together.  Mode 1 offsets them once
+        // per launch; the offset then drifts back to in-phase within ~20 iterations (measured, tools/att_offsets.py), so
+        // mode 2 re-establishes it at the first tile of every two-slot unit: slot 1 starts its softmax when slot 0 has
+        // stored the first half of its P tile.
+        if (kStaggerNow) {
           if (slot == 1) named_bar_sync(1, 2 * BQ);
           else if (!warp_valid) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
         }
@@ -523,7 +528,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
             exp_chunk<true>(sv[1], c, neg_m, b0, b1, pk1);
             tmem_st16(p_addr + 16, pk1);
 #if STAD_ATT_STAGGER
-            if (g == 0 && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+            if (kStaggerNow && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
 #endif
 #else
             const bool o_ok = pv_done || mbar_try_wait(&o_full[slot], (g - 1) & 1);
@@ -627,7 +632,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
           }
           l_sum += a0 + a1;
 #if STAD_ATT_STAGGER
-          if (g == 0 && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+          if (kStaggerNow && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
 #endif
           tc_fence_before();
           __syncwarp();

@@ -59,11 +59,20 @@ STAD_DEVICE void exp_chunk(const uint32_t (&s)[32], float c, float neg_m, float&
   }
 }
 
+// Row max of one 32-column chunk: four independent FMNMX3 chains (a single chain of 16 dependent three-input maxima is
+// latency-bound: ~5 clk per step, and the row max sits on the critical path of every tile).
 STAD_DEVICE float chunk_max(const uint32_t (&s)[32]) {
-  float m = max3(__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]));
+  float m[4];
 #pragma unroll
-  for (int i = 3; i < 31; i += 2) m = max3(m, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-  return fmaxf(m, __uint_as_float(s[31]));
+  for (int k = 0; k < 4; ++k)
+    m[k] = max3(__uint_as_float(s[8 * k]), __uint_as_float(s[8 * k + 1]), __uint_as_float(s[8 * k + 2]));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    m[k] = max3(m[k], __uint_as_float(s[8 * k + 3]), __uint_as_float(s[8 * k + 4]));
+    m[k] = max3(m[k], __uint_as_float(s[8 * k + 5]), __uint_as_float(s[8 * k + 6]));
+  }
+  return fmaxf(max3(m[0], m[1], __uint_as_float(s[7])), max3(max3(m[2], m[3], __uint_as_float(s[15])),
+                                                             __uint_as_float(s[23]), __uint_as_float(s[31])));
 }
 
 }  // namespace stad

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import modeling_finetune  # noqa: F401  (registers the vit_* factories, as `import modeling_finetune` does at te:9)
 from .registry import create_model
 
 MODEL_NAMES = {"VideoMAE-S": "vit_small_patch16_224", "VideoMAE-B": "vit_base_patch16_224",
