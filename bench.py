@@ -41,6 +41,19 @@ def parse_args():
     return ap.parse_args()
 
 
+def load_ncu_traffic(model_name, B):
+    """DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+    capture of this workload (profiles/ncu_gemm_dram.json, written by tools/ncu_dram_summary.py); None when the capture
+    is for another model / batch."""
+    path = os.path.join(ROOT, "profiles", "ncu_gemm_dram.json")
+    if not os.path.exists(path):
+        return None
+    d = json.load(open(path))
+    if d.get("model") != model_name or d.get("batch") != B:
+        return None
+    return d
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -280,7 +293,7 @@ def main():
     peak = peaks["bf16_tflops_sustained"]  # kernels timed inside a long step -> sustained figure
     roofline = {
         "bound": "tensor", "kernel": "gemm_kernel (tcgen05, all epilogues)", "achieved": gemm_tflops, "peak": peak,
-        "unit": "TFLOP/s", "frac": gemm_tflops / peak, "traffic": None,
+        "unit": "TFLOP/s", "frac": gemm_tflops / peak, "traffic": None, "traffic_unit": "bytes per launch",
         "peak_source": peaks["source"] + ", sustained cuBLAS bf16",
         "launches_per_step": gemm["launches"] / args.steps, "avg_launch_ms": gemm["ms"] / max(1, gemm["launches"]),
         "share_of_step": gemm["ms"] / total_kernel_ms,
@@ -290,21 +303,38 @@ def main():
         "other_share_of_step": {k: v["ms"] / total_kernel_ms for k, v in by_kind.items() if k not in ("gemm", "attention")},
     }
 
+    ncu = load_ncu_traffic(args.model, B)
+    if ncu is not None:
+        # weighted by how often each GEMM shape launches in a step (1 patch embed + depth x {qkv, proj, fc1, fc2})
+        per = ncu["dram_bytes_per_launch"]
+        tot = per["patch_embed"] + depth * (per["qkv"] + per["proj"] + per["fc1"] + per["fc2"])
+        roofline["traffic"] = tot / (1 + 4 * depth)
+        alg = ncu["algorithmic_bytes_per_launch"]
+        roofline["traffic_detail"] = {"dram_bytes_per_launch": per, "algorithmic_bytes_per_launch": alg,
+                                      "source": ncu["source"]}
+
     # ---------------------------------------------------------------- end to end through the public runner API
+    # Host frames as the reference's callers hold them after cv2.resize (uint8 HWC BGR, ri:79-81): every step copies
+    # them host->device from pinned memory, normalises on the device (prepare_image, ri:15-34), scores the B windows
+    # and reads (logits, probs) back to the host.
+    gen = torch.Generator().manual_seed(77 + rank)
+    host_u8 = [torch.randint(0, 256, (T_frames, 224, 224, 3), generator=gen, dtype=torch.uint8).pin_memory()
+               for _ in range(n_bufs)]
     e2e_steps = max(3, min(args.steps, 10))
-    runner.score_frames(host_videos[0])
+    runner.score_frames_u8(host_u8[0], bgr=True)
     sync_all()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        lg, pr = runner.score_frames(host_videos[i % n_bufs])  # pinned host frames in, host scores out
+        lg, pr = runner.score_frames_u8(host_u8[i % n_bufs], bgr=True)  # pinned host frames in, host scores out
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    h2d = host_videos[0].numel() * host_videos[0].element_size()
+    h2d = host_u8[0].numel() * host_u8[0].element_size()
     d2h = 2 * B * 2 * 4
+    e2e_launches = prep.last_launches + 1  # + the uint8 normalise kernel
 
     clips_per_s = world * B * args.steps / (ms_total * 1e-3)
     model_tflops = clips_per_s / world * GFLOP_PER_CLIP[args.model] / 1e3
@@ -321,7 +351,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "clips/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "api": "SlidingWindowRunner.score_frames(pinned fp32 frames) -> host (logits, probs)"},
+                "gpu_launches_per_step": e2e_launches,
+                "api": "SlidingWindowRunner.score_frames_u8(pinned uint8 HWC BGR frames) -> host (logits, probs)"},
         "gpu_launches": launches_per_step * args.steps,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
