@@ -145,7 +145,7 @@ STAD_API const char* stad_last_error(void);
 enum {
   STAD_K_CAST = 0, STAD_K_GATHER = 1, STAD_K_GEMM = 2, STAD_K_ATTENTION = 3, STAD_K_ROW_STATS = 4,
   STAD_K_LAYERNORM = 5, STAD_K_POOL = 6, /* ROW_STATS with epi = 1: stad_stats_finalize */
-  STAD_K_ASSEMBLE = 7, STAD_K_TAIL = 8, STAD_K_NORMALIZE = 9
+  STAD_K_ASSEMBLE = 7, STAD_K_TAIL = 8, STAD_K_NORMALIZE = 9, STAD_K_EVAL = 10
 };
 typedef struct stad_profile_record {
   int32_t kind;    /* STAD_K_*                                                        */
@@ -256,6 +256,19 @@ STAD_API int stad_mae_forward(const stad_mae_model* model, const stad_input* in,
  * mean / std: HOST float[3] (RGB order).  The output is the frame buffer stad_input (STAD_IN_FRAMES) reads. */
 STAD_API int stad_normalize_frames_u8(const void* frames_u8, void* out_bf16, int F, int H, int W, const float* mean,
                                       const float* std, int bgr, stad_stream_t stream);
+
+/* ---- evaluation epilogue ------------------------------------------------------------------------------------------ */
+/* Confusion counts of the per-frame risk probability probs[i][1] against T ascending fp32 thresholds
+ * (engine_for_frame_finetuning.py:461-488 evaluates torchmetrics' binned AUROC / AP / PR / ROC on THRESHOLDS =
+ * arange(0, 1.001, 0.01); anaysis/metrics.py:183-199 evaluates MCC / P / R / acc / F1 at every one of them).
+ *   probs[n, 2] fp32 (softmax output of stad_vit_forward), labels int32[n] (non-zero = anomalous),
+ *   hist  uint64[2][T + 1]: hist[y][b] = number of samples of label y with exactly b thresholds <= p, so
+ *         TP_k = sum_{b > k} hist[1][b],  FP_k = sum_{b > k} hist[0][b]   (prediction `p >= t_k`, as the reference);
+ *   conf  uint64[4] = tn, fp, fn, tp of the arg-max prediction (torch.max(softmax, 1), eff:464).
+ * Counts are exact integers, additive over shards: ranks all-reduce (SUM) the two small tables instead of gathering
+ * every prediction.  hist and conf are zeroed by the call. */
+STAD_API int stad_eval_hist(const float* probs, const int32_t* labels, long long n, const float* thresholds, int T,
+                            unsigned long long* hist, unsigned long long* conf, stad_stream_t stream);
 
 #ifdef __cplusplus
 }

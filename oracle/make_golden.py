@@ -218,6 +218,28 @@ def gen_masks(name):
     save(name, **out)
 
 
+def gen_eval_metrics(name):
+    """anaysis/metrics.py `calculate_MORE_metrics` of the unmodified reference (scikit-learn) on synthetic scores."""
+    from anaysis import metrics as ref_metrics
+    from oracle import metrics_oracle as mo
+    out = {}
+    for seed, n in ((0, 5000), (1, 257)):
+        logits, labels = mo.synthetic_scores(n, seed=seed)
+        probs = torch.from_numpy(logits).softmax(-1).numpy()     # fp32, as final_test holds them (eff:461-462)
+        r = ref_metrics.calculate_MORE_metrics(probs[:, 1], labels)
+        (acc, prec, rec, f1, ap, auroc, confmat, _pr, _roc, mcc_t, p_t, r_t, acc_t, f1_t) = r
+        mine, _ = mo.thresholded(probs[:, 1], labels)
+        for k, ref_list in (("mcc", mcc_t), ("precision", p_t), ("recall", r_t), ("acc", acc_t), ("f1", f1_t)):
+            assert np.allclose(mine[k], ref_list, atol=1e-12), f"oracle thresholded {k} differs from the reference"
+        b = mo.torchmetrics_binned(probs[:, 1], labels)
+        print(f"{name}[seed {seed}, n {n}]: sklearn auroc {auroc:.6f} ap {ap:.6f}; binned(101) auroc {b['auroc']:.6f} ap {b['ap']:.6f}")
+        out.update({f"probs_s{seed}": probs, f"labels_s{seed}": labels, f"mcc_s{seed}": np.array(mcc_t),
+                    f"precision_s{seed}": np.array(p_t), f"recall_s{seed}": np.array(r_t), f"acc_s{seed}": np.array(acc_t),
+                    f"f1_s{seed}": np.array(f1_t), f"at05_s{seed}": np.array([acc, prec, rec, f1]),
+                    f"confmat_s{seed}": np.array(confmat), f"sk_auroc_ap_s{seed}": np.array([auroc, ap])})
+    save(name, **out)
+
+
 def main():
     install_shims()
     torch.set_num_threads(os.cpu_count())
@@ -231,6 +253,7 @@ def main():
         gen_encoder("small_enc_vitb_d2_b2", "vit_base_d2", B=2, seed=12)
         gen_pretrain("small_mae_vits_d2_b2", "vit_small_d2", B=2, seed=14, decoder_depth=2)
         gen_masks("tube_masks")
+        gen_eval_metrics("eval_metrics")
     if on("peaky"):
         gen_classifier("peaky_vits_d2_b2", "vit_small_d2", B=2, seed=13, peaky=3.0)
     # the five BASELINE.json configs

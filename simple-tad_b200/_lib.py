@@ -18,7 +18,7 @@ EXPORTS = (
     "stad_pool_norm_head", "stad_patch_embed", "stad_ln_gemm", "stad_gemm_bias_residual", "stad_attention",
     "stad_workspace_bytes", "stad_vit_forward", "stad_profile_enable", "stad_profile_read", "stad_stat_parts",
     "stad_gemm_bias_residual_stats", "stad_stats_finalize", "stad_decoder_assemble", "stad_tail_rows_f32",
-    "stad_mae_workspace_bytes", "stad_mae_forward", "stad_normalize_frames_u8",
+    "stad_mae_workspace_bytes", "stad_mae_forward", "stad_normalize_frames_u8", "stad_eval_hist",
 )
 
 
@@ -60,7 +60,7 @@ class StadProfileRecord(C.Structure):
 
 
 KIND_NAMES = {0: "cast", 1: "gather", 2: "gemm", 3: "attention", 4: "row_stats", 5: "layernorm", 6: "pool",
-              7: "assemble", 8: "tail", 9: "normalize"}
+              7: "assemble", 8: "tail", 9: "normalize", 10: "eval"}
 
 _lib = None
 _inited_devices = set()
@@ -103,6 +103,7 @@ def load():
         "stad_mae_forward": (C.c_int, [C.POINTER(StadMaeModel), C.POINTER(StadInput), vp, vp, i32, i32, vp, vp, sz, vp]),
         "stad_normalize_frames_u8": (C.c_int, [vp, vp, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), i32,
                                                vp]),
+        "stad_eval_hist": (C.c_int, [vp, vp, C.c_longlong, vp, i32, vp, vp, vp]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -349,3 +350,20 @@ def normalize_frames_u8(frames, mean, std, bgr=False, out=None):
     check(load().stad_normalize_frames_u8(ptr(frames), ptr(out), F_, H, W, m, sd, int(bool(bgr)), stream_ptr()),
           "stad_normalize_frames_u8")
     return out
+
+
+def eval_hist(probs, labels, thresholds):
+    """probs [n, 2] fp32, labels int32 [n], thresholds fp32 [T] ascending -> (hist int64 [2, T+1], conf int64 [4]):
+    the exact threshold histogram / arg-max confusion counts of stad_eval_hist (eff:461-488)."""
+    init(probs.device)
+    _req(probs, torch.float32, "probs")
+    _req(labels, torch.int32, "labels")
+    _req(thresholds, torch.float32, "thresholds")
+    n, T = probs.shape[0], thresholds.numel()
+    if probs.dim() != 2 or probs.shape[1] != 2 or labels.numel() != n:
+        raise ValueError(f"eval_hist: probs {tuple(probs.shape)}, labels {tuple(labels.shape)}")
+    hist = torch.empty(2, T + 1, dtype=torch.int64, device=probs.device)
+    conf = torch.empty(4, dtype=torch.int64, device=probs.device)
+    check(load().stad_eval_hist(ptr(probs), ptr(labels), n, ptr(thresholds), T, ptr(hist), ptr(conf), stream_ptr()),
+          "stad_eval_hist")
+    return hist, conf

@@ -506,4 +506,10 @@ int stad_mae_forward(const stad_mae_model* m, const stad_input* in, const int32_
   return launches;
 }
 
+int stad_eval_hist(const float* probs, const int32_t* labels, long long n, const float* thresholds, int T,
+                   unsigned long long* hist, unsigned long long* conf, stad_stream_t stream) {
+  STAD_CHECK_ARG(probs && labels && thresholds && hist && conf, "eval_hist: NULL argument");
+  return launch_eval_hist(probs, labels, n, thresholds, T, hist, conf, as_stream(stream));
+}
+
 }  // extern "C"

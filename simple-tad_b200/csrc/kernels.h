@@ -66,4 +66,8 @@ int launch_tail_rows_f32(const bf16* x, float* y, int B, int N, int n_keep, int 
 int launch_normalize_u8(const uint8_t* in, bf16* out, int F, int H, int W, const float* mean, const float* std_, int bgr,
                         cudaStream_t stream);
 
+// evaluation epilogue: threshold histogram of the risk probabilities (engine_for_frame_finetuning.py:461-488)
+int launch_eval_hist(const float* probs, const int32_t* labels, long long n, const float* thresholds, int T,
+                     unsigned long long* hist, unsigned long long* conf, cudaStream_t stream);
+
 }  // namespace stad

@@ -381,6 +381,47 @@ normalize_u8_kernel(const uint8_t* __restrict__ in, bf16* __restrict__ out, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Evaluation epilogue (engine_for_frame_finetuning.py:461-488, anaysis/metrics.py:183-199): confusion counts of the
+// per-frame risk probability against T ascending thresholds, one pass over the n scores.
+// For a sample with probability p the number b of thresholds with t_k <= p (found by binary search with exactly the
+// fp32 comparisons `p >= t_k` the reference makes) puts it into bin b of its label's histogram; the prediction at
+// threshold k is positive iff b > k, so TP_k / FP_k are suffix sums of the two histograms.  Integer arithmetic
+// throughout: the counts are exact and independent of the summation order (integer atomics).
+// hist: [2][T + 1] (label, bin); conf: [4] = tn, fp, fn, tp of the arg-max prediction (eff:464, ties -> class 0).
+// Bytes: 12 n read.
+constexpr int kMaxThresholds = 1024;
+__global__ void __launch_bounds__(256)
+eval_hist_kernel(const float* __restrict__ probs, const int32_t* __restrict__ labels, long long n,
+                 const float* __restrict__ thresholds, int T, unsigned long long* __restrict__ hist,
+                 unsigned long long* __restrict__ conf) {
+  extern __shared__ unsigned int sh[];  // [T] thresholds as float bits, then [2][T + 1] counts, then [4] arg-max conf
+  float* th = reinterpret_cast<float*>(sh);
+  unsigned int* cnt = sh + T;
+  unsigned int* cf = cnt + 2 * (T + 1);
+  for (int i = threadIdx.x; i < T; i += blockDim.x) th[i] = thresholds[i];
+  for (int i = threadIdx.x; i < 2 * (T + 1) + 4; i += blockDim.x) cnt[i] = 0u;
+  __syncthreads();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float2 p = __ldg(reinterpret_cast<const float2*>(probs) + i);
+    const int y = __ldg(labels + i) != 0;
+    int lo = 0, hi = T;  // b = #{k : th[k] <= p.y}; thresholds ascending
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (p.y >= th[mid]) lo = mid + 1;
+      else hi = mid;
+    }
+    atomicAdd(&cnt[y * (T + 1) + lo], 1u);
+    const int pred = p.y > p.x;  // torch.max(softmax, 1): first maximum wins, so a tie predicts class 0
+    atomicAdd(&cf[y * 2 + pred], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * (T + 1); i += blockDim.x)
+    if (cnt[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(cnt[i]));
+  if (threadIdx.x < 4 && cf[threadIdx.x]) atomicAdd(&conf[threadIdx.x], static_cast<unsigned long long>(cf[threadIdx.x]));
+}
+
 }  // namespace
 
 int launch_cast_f32_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream) {
@@ -524,6 +565,24 @@ int launch_normalize_u8(const uint8_t* in, bf16* out, int F, int H, int W, const
   normalize_u8_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
       in, out, HW, HW >> 3, total, na, bgr);
   STAD_LAUNCH_OK("normalize_u8");
+  return STAD_OK;
+}
+
+int launch_eval_hist(const float* probs, const int32_t* labels, long long n, const float* thresholds, int T,
+                     unsigned long long* hist, unsigned long long* conf, cudaStream_t stream) {
+  STAD_CHECK_ARG(n > 0 && T >= 1 && T <= kMaxThresholds, "eval_hist: n=%lld T=%d (T <= %d)", n, T, kMaxThresholds);
+  if ((reinterpret_cast<uintptr_t>(probs) | reinterpret_cast<uintptr_t>(hist) | reinterpret_cast<uintptr_t>(conf)) & 7)
+    return fail(STAD_E_ALIGN, "eval_hist: probs, hist, conf must be 8-byte aligned");
+  const int threads = 256;
+  long long blocks = (n + threads * 8 - 1) / (threads * 8);
+  const long long cap = static_cast<long long>(sm_count()) * 4;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = (static_cast<size_t>(T) + 2 * (T + 1) + 4) * sizeof(unsigned int);
+  STAD_CUDA_OK(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * 2 * (T + 1), stream));
+  STAD_CUDA_OK(cudaMemsetAsync(conf, 0, sizeof(unsigned long long) * 4, stream));
+  ProfScope prof(STAD_K_EVAL, 0, static_cast<int>(n >> 10), T, 0, stream);
+  eval_hist_kernel<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(probs, labels, n, thresholds, T, hist, conf);
+  STAD_LAUNCH_OK("eval_hist");
   return STAD_OK;
 }
 

@@ -1,0 +1,140 @@
+"""Evaluation epilogue of frame-level inference — the metrics `final_test` computes after the score gather
+(engine_for_frame_finetuning.py:448-497) and the per-threshold tables of anaysis/metrics.py:133-207.
+
+The reduction over the n per-frame scores runs on the device (`stad_eval_hist`: one pass, exact integer counts against
+the 101 THRESHOLDS); what is left is arithmetic on a [2, 102] integer table, done here in float64.  The counts are
+additive, so under torchrun the ranks all-reduce that table (808 + 32 bytes) instead of gathering every prediction the
+way `gather_predictions_nontensor` (utils.py:791-810) does; the gathered logits are only needed for predictions.csv.
+
+Definitions follow the libraries the reference calls:
+  * torchmetrics (binary, `thresholds=THRESHOLDS`, eff:469-488): confusion matrices at `p >= t`; ROC = (fpr, tpr)
+    flipped to ascending fpr; AUROC = trapezoid; PR curve with the (precision 1, recall 0) end point; AP =
+    -sum((r[1:] - r[:-1]) * p[:-1]).  torchmetrics is not pinned by the reference (INSTALL.md:27) and not installed
+    here: this is a restatement of its published binned algorithm (v1.x), see DESIGN.md.
+  * sklearn (anaysis/metrics.py:183-199): precision / recall / F1 with zero_division=0, accuracy, Matthews
+    correlation at every threshold.
+"""
+import csv
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+THRESHOLDS = np.arange(0.00, 1.001, 0.01).tolist()  # anaysis/metrics.py:16 (eff:22)
+
+
+def threshold_tensor(device, thresholds=THRESHOLDS):
+    """The thresholds as the fp32 values the reference's `probs >= t` comparison sees for fp32 probabilities."""
+    return torch.tensor(np.asarray(thresholds, dtype=np.float64).astype(np.float32), device=device)
+
+
+def counts_from_hist(hist):
+    """hist int64 [2, T+1] (label, number of thresholds <= p) -> dict of int64 [T] arrays tn, fp, fn, tp for the
+    predictions `p >= t_k`: positive at threshold k  <=>  bin > k."""
+    h = np.asarray(hist, dtype=np.int64)
+    above = h[:, ::-1].cumsum(axis=1)[:, ::-1]          # above[y, b] = sum_{b' >= b} h[y, b']
+    fp, tp = above[0, 1:], above[1, 1:]                 # bin > k  <=>  bin >= k + 1
+    n_neg, n_pos = h[0].sum(), h[1].sum()
+    return {"tn": n_neg - fp, "fp": fp, "fn": n_pos - tp, "tp": tp}
+
+
+def _div(a, b, zero=0.0):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    out = np.full(np.broadcast(a, b).shape, zero, dtype=np.float64)
+    np.divide(a, b, out=out, where=b != 0)
+    return out
+
+
+def thresholded_metrics(c):
+    """MCC / precision / recall / accuracy / F1 at every threshold (anaysis/metrics.py:183-199; sklearn definitions with
+    zero_division=0; MCC = 0 when a marginal is empty, as sklearn.metrics.matthews_corrcoef returns)."""
+    tn, fp, fn, tp = (c[k].astype(np.float64) for k in ("tn", "fp", "fn", "tp"))
+    n = tn + fp + fn + tp
+    # sklearn's covariance form: cov_ytyp / sqrt(cov_ytyt * cov_ypyp) on the 2x2 confusion matrix
+    t_pos, t_neg, p_pos, p_neg = tp + fn, tn + fp, tp + fp, tn + fn
+    cov_ytyp = (tp + tn) * n - (t_pos * p_pos + t_neg * p_neg)
+    cov_ypyp = n * n - (p_pos * p_pos + p_neg * p_neg)
+    cov_ytyt = n * n - (t_pos * t_pos + t_neg * t_neg)
+    return {"mcc": _div(cov_ytyp, np.sqrt(cov_ytyt * cov_ypyp)), "precision": _div(tp, tp + fp),
+            "recall": _div(tp, tp + fn), "acc": _div(tp + tn, n), "f1": _div(2 * tp, 2 * tp + fp + fn)}
+
+
+def binned_curves(c, thresholds=THRESHOLDS):
+    """torchmetrics' binned ROC / PR curves and their summaries (eff:469-488)."""
+    tn, fp, fn, tp = (c[k].astype(np.float64) for k in ("tn", "fp", "fn", "tp"))
+    thr = np.asarray(thresholds, dtype=np.float64)
+    tpr, fpr = _div(tp, tp + fn)[::-1], _div(fp, fp + tn)[::-1]
+    auroc = float(np.sum((fpr[1:] - fpr[:-1]) * (tpr[1:] + tpr[:-1]) / 2.0))
+    precision = np.concatenate([_div(tp, tp + fp), [1.0]])
+    recall = np.concatenate([_div(tp, tp + fn), [0.0]])
+    ap = float(-np.sum((recall[1:] - recall[:-1]) * precision[:-1]))
+    return {"auroc": auroc, "ap": ap, "roc_curve": (fpr, tpr, thr[::-1].copy()), "pr_curve": (precision, recall, thr)}
+
+
+def argmax_metrics(conf):
+    """Accuracy / recall / precision / F1 / confusion matrix of the arg-max prediction (eff:464-468)."""
+    tn, fp, fn, tp = (float(v) for v in conf)
+    n = tn + fp + fn + tp
+    d = lambda a, b: a / b if b else 0.0  # noqa: E731
+    return {"acc": d(tp + tn, n), "recall": d(tp, tp + fn), "precision": d(tp, tp + fp), "f1": d(2 * tp, 2 * tp + fp + fn),
+            "confmat": [[int(tn), int(fp)], [int(fn), int(tp)]]}
+
+
+@torch.no_grad()
+def evaluate(probs, labels, thresholds=THRESHOLDS, group=None):
+    """probs [n, 2] fp32 CUDA (softmax of the logits), labels [n] (any integer dtype) -> dict with the metrics of
+    `final_test` (mAP, auroc, acc, P/R/F1 @ arg-max, confmat, binned PR / ROC curves) and the per-threshold lists of
+    anaysis/metrics.py.  Under an initialised process group every rank passes ITS shard and receives the metrics of
+    the whole set (one all-reduce of the count tables)."""
+    if not probs.is_cuda:
+        raise RuntimeError("simple-tad_b200 runs on a CUDA (sm_100a) device only; got CPU scores")
+    probs = probs.float().contiguous()
+    labels = labels.to(device=probs.device, dtype=torch.int32).contiguous()
+    if probs.shape[0] > 0:
+        hist, conf = _lib.eval_hist(probs, labels, threshold_tensor(probs.device, thresholds))
+    else:  # an empty shard (more ranks than windows) still takes part in the reduction below
+        hist = torch.zeros(2, len(thresholds) + 1, dtype=torch.int64, device=probs.device)
+        conf = torch.zeros(4, dtype=torch.int64, device=probs.device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        packed = torch.cat([hist.flatten(), conf])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        hist, conf = packed[:-4].view_as(hist), packed[-4:]
+    c = counts_from_hist(hist.cpu().numpy())
+    res = {"counts": c, "n": int(hist.sum())}
+    res.update(argmax_metrics(conf.cpu().numpy()))
+    res.update(binned_curves(c, thresholds))
+    res["thresholded"] = thresholded_metrics(c)
+    return res
+
+
+def stats_lines(res):
+    """The block `final_test` prints and writes to stats.txt (eff:489-493)."""
+    cm = res["confmat"]
+    return ["\n===================================",
+            f"mAP: {res['ap']}, auroc: {res['auroc']}, acc: {res['acc']}",
+            f"P@0.5: {res['precision']}, R@0.5: {res['recall']}, F1@0.5: {res['f1']}",
+            f"Confmat: \n\t{cm[0][0]} | {cm[0][1]} \n\t{cm[1][0]} | {cm[1][1]}",
+            "----------------------------"]
+
+
+def write_stats(stats_file, res):
+    with open(stats_file, "w") as f:
+        for line in stats_lines(res):
+            f.write(line + "\n")
+
+
+def write_predictions_csv(preds_file, clips, filenames, logits, labels, ttcs):
+    """predictions.csv with the columns of eff:525-533 (index, clip, filename, logits_safe, logits_risk, label, ttc),
+    readable by the reference's anaysis/ scripts."""
+    logits = torch.as_tensor(logits).detach().float().cpu().numpy()
+    labels = torch.as_tensor(labels).detach().cpu().numpy().astype(int)
+    ttcs = torch.as_tensor(ttcs).detach().cpu().numpy()
+    with open(preds_file, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["", "clip", "filename", "logits_safe", "logits_risk", "label", "ttc"])
+        for i in range(len(labels)):
+            w.writerow([i, clips[i], filenames[i], repr(float(logits[i, 0])), repr(float(logits[i, 1])), int(labels[i]),
+                        repr(float(ttcs[i]))])

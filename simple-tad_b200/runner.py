@@ -140,3 +140,35 @@ class SlidingWindowRunner:
         C = self.model.num_classes
         local = torch.cat(outs) if outs else torch.zeros(0, C, dtype=torch.float32, device=self.device)
         return gather_scores(local, n_total, group)
+
+    @torch.no_grad()
+    def evaluate_videos(self, videos, frame_labels, group=None):
+        """`final_test` (eff:385-497) for a list of videos: frame_labels[v] is the per-frame 0/1 label tensor [T_v] of
+        video v; window w of a video is labelled by its last frame (dota.py:217-223).  Returns (metrics, logits):
+        the metrics of simple_tad_b200.metrics.evaluate over ALL windows (each rank reduces its own shard on the device,
+        the ranks all-reduce the 2 x 102 count table) and the gathered logits [n_windows, num_classes] for
+        predictions.csv."""
+        from . import metrics as M
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        lengths = [int(v.shape[0]) for v in videos]
+        _, n_total = window_segments(lengths, 0, 0, self.T, self.stride)
+        lo, hi, per = shard_range(n_total, world, rank)
+        segs, _ = window_segments(lengths, lo, hi, self.T, self.stride)
+        outs, labs = [], []
+        for v, w0, cnt in segs:
+            f0 = w0 * self.stride
+            f1 = (w0 + cnt - 1) * self.stride + self.T
+            lg, _ = self.score_frames_device(videos[v][f0:f1])
+            outs.append(lg.clone())
+            last = torch.arange(w0, w0 + cnt) * self.stride + self.T - 1
+            labs.append(torch.as_tensor(frame_labels[v])[last].to(torch.int32))
+        C = self.model.num_classes
+        if outs:
+            local = torch.cat(outs)
+            local_labels = torch.cat(labs).to(self.device)
+        else:  # more ranks than windows: an empty shard still takes part in the reductions
+            local = torch.zeros(0, C, dtype=torch.float32, device=self.device)
+            local_labels = torch.zeros(0, dtype=torch.int32, device=self.device)
+        res = M.evaluate(local.softmax(-1), local_labels, group=group)
+        return res, gather_scores(local, n_total, group)

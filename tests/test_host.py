@@ -142,6 +142,38 @@ def test_norm_fold_of_the_pixel_head_is_exact():
         assert float((got - ref).abs().max()) < 2e-2 * float(ref.abs().max())
 
 
+def test_metrics_host_math_from_histogram_matches_the_oracle():
+    """simple_tad_b200.metrics: suffix sums of the threshold histogram -> confusion counts -> every metric, against the
+    oracle's per-threshold loops (the histogram the kernel produces is emulated here with numpy.searchsorted)."""
+    from oracle import metrics_oracle as mo
+    from simple_tad_b200 import metrics as M
+    assert M.THRESHOLDS == mo.THRESHOLDS and len(M.THRESHOLDS) == 101
+    logits, labels = mo.synthetic_scores(3000, seed=5)
+    probs = torch.from_numpy(logits).softmax(-1).numpy()
+    thr32 = np.asarray(M.THRESHOLDS, dtype=np.float64).astype(np.float32)
+    bins = np.searchsorted(thr32, probs[:, 1], side="right")           # number of thresholds <= p
+    hist = np.zeros((2, 102), dtype=np.int64)
+    np.add.at(hist, (labels, bins), 1)
+    c = M.counts_from_hist(hist)
+    th, counts = mo.thresholded(probs[:, 1], labels, thr32)
+    for i, k in enumerate(("tn", "fp", "fn", "tp")):
+        assert np.array_equal(c[k], counts[:, i]), k
+    got = M.thresholded_metrics(c)
+    for k in ("mcc", "precision", "recall", "acc", "f1"):
+        np.testing.assert_allclose(got[k], th[k], atol=1e-12, rtol=0)
+    b, ob = M.binned_curves(c), mo.torchmetrics_binned(probs[:, 1], labels)
+    assert abs(b["auroc"] - ob["auroc"]) < 1e-12 and abs(b["ap"] - ob["ap"]) < 1e-12
+    np.testing.assert_allclose(b["roc_curve"][0], ob["fpr"], atol=1e-15)
+    np.testing.assert_allclose(b["pr_curve"][0], ob["precision"], atol=1e-15)
+    pred = probs[:, 1] > probs[:, 0]
+    conf = [int((~pred & (labels == 0)).sum()), int((pred & (labels == 0)).sum()), int((~pred & (labels == 1)).sum()),
+            int((pred & (labels == 1)).sum())]
+    a, oa = M.argmax_metrics(conf), mo.argmax_metrics(probs, labels)
+    assert a == oa
+    lines = M.stats_lines({**a, **b})
+    assert lines[1].startswith("mAP: ") and "auroc: " in lines[1] and lines[3].startswith("Confmat: ")
+
+
 def test_inference_only_and_cuda_only():
     m = mf.vit_small_patch16_224(num_classes=2)
     with pytest.raises((NotImplementedError, RuntimeError)):

@@ -225,6 +225,68 @@ def test_efficiency_harness_and_cuda_graph_replay():
     assert [r["batch_per_gpu"] for r in rows] == [1, 3] and all(r["clips_per_s"] > 0 for r in rows)
 
 
+def test_eval_epilogue_counts_are_exact_and_metrics_match_the_reference():
+    """stad_eval_hist + simple_tad_b200.metrics.evaluate vs (1) the golden outputs of the reference's anaysis/metrics.py
+    (scikit-learn), (2) the oracle's per-threshold loops: integer counts bit-exact, metrics to 1e-12; plus a 3M-sample
+    run checked through size-independent properties (count totals, monotone suffix sums, numpy.searchsorted)."""
+    import numpy as np
+    from oracle import metrics_oracle as mo
+    from simple_tad_b200 import _lib, metrics as M
+    g = parity.golden("eval_metrics")
+    for seed in (0, 1):
+        probs, labels = g[f"probs_s{seed}"], g[f"labels_s{seed}"]
+        res = M.evaluate(torch.from_numpy(probs).to(DEV), torch.from_numpy(labels).to(DEV))
+        th, counts = mo.thresholded(probs[:, 1], labels, np.asarray(M.THRESHOLDS).astype(np.float32))
+        for i, k in enumerate(("tn", "fp", "fn", "tp")):
+            assert np.array_equal(res["counts"][k], counts[:, i]), f"seed {seed}: {k} counts differ"
+        for k in ("mcc", "precision", "recall", "acc", "f1"):
+            np.testing.assert_allclose(res["thresholded"][k], g[f"{k}_s{seed}"], atol=1e-12, rtol=0)
+        oa = mo.argmax_metrics(probs, labels)
+        assert res["confmat"] == oa["confmat"] and abs(res["f1"] - oa["f1"]) < 1e-15
+        ob = mo.torchmetrics_binned(probs[:, 1], labels)
+        assert abs(res["auroc"] - ob["auroc"]) < 1e-12 and abs(res["ap"] - ob["ap"]) < 1e-12
+        assert res["n"] == len(labels)
+    # large n: probabilities straight from a softmax on the device, labels random
+    n = 3_000_000
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    lg = torch.randn(n, 2, generator=gen, device=DEV) * 3
+    pr = lg.softmax(-1).contiguous()
+    lb = (torch.rand(n, generator=gen, device=DEV) < 0.2).to(torch.int32)
+    thr = M.threshold_tensor(DEV)
+    hist, conf = _lib.eval_hist(pr, lb, thr)
+    assert int(hist.sum()) == n and int(conf.sum()) == n
+    bins = torch.searchsorted(thr, pr[:, 1].contiguous(), right=True)
+    ref = torch.zeros(2, 102, dtype=torch.int64, device=DEV)
+    ref.view(-1).index_add_(0, lb.long() * 102 + bins, torch.ones(n, dtype=torch.int64, device=DEV))
+    assert torch.equal(hist, ref)
+    assert int(conf[1] + conf[3]) == int((pr[:, 1] > pr[:, 0]).sum())
+    c = M.counts_from_hist(hist.cpu().numpy())
+    assert (np.diff(c["tp"]) <= 0).all() and (np.diff(c["fp"]) <= 0).all() and c["tp"][0] + c["fn"][0] == int(lb.sum())
+
+
+def test_runner_evaluate_videos_matches_metrics_on_the_gathered_scores():
+    """final_test shape (eff:385-497): sliding-window scores of several videos + frame labels -> metrics; the device
+    reduction over the runner's shard equals the oracle's metrics on the same scores."""
+    import numpy as np
+    from oracle import metrics_oracle as mo
+    from simple_tad_b200.runner import SlidingWindowRunner
+    sd = synth.make_state_dict("vit_small_d2", seed=11)
+    model = parity.build_classifier("vit_small_d2", sd)
+    videos = [synth.make_video(T, seed=40 + i) for i, T in enumerate((22, 16, 30))]
+    gen = torch.Generator().manual_seed(1)
+    labels = [(torch.rand(v.shape[0], generator=gen) < 0.4).long() for v in videos]
+    runner = SlidingWindowRunner(model, batch_windows=8)
+    res, logits = runner.evaluate_videos(videos, labels)
+    n = sum(v.shape[0] - 15 for v in videos)
+    assert logits.shape == (n, 2) and res["n"] == n
+    win_labels = np.concatenate([l[15:].numpy() for l in labels])
+    probs = logits.softmax(-1).cpu().numpy()
+    th, counts = mo.thresholded(probs[:, 1], win_labels, np.asarray(mo.THRESHOLDS).astype(np.float32))
+    assert np.array_equal(res["counts"]["tp"], counts[:, 3]) and np.array_equal(res["counts"]["fp"], counts[:, 1])
+    assert res["confmat"] == mo.argmax_metrics(probs, win_labels)["confmat"]
+    np.testing.assert_allclose(res["thresholded"]["mcc"], th["mcc"], atol=1e-12)
+
+
 def test_config5_batch_sweep_consistency():
     """BASELINE config 5 (correctness side of the batch sweep): ViT-B logits for the same clips at batch 1, 2, 8
     all match the reference within tolerance."""

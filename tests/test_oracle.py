@@ -121,6 +121,34 @@ def test_tube_masking_generator_matches_reference_draws():
     assert gen.total_masks == 8 * 176 and gen.num_visible == 160 and "mask patches 1408" in repr(gen)
 
 
+def test_eval_metrics_oracle_matches_reference_metrics_py():
+    """oracle/metrics_oracle.py vs the unmodified anaysis/metrics.py `calculate_MORE_metrics` (scikit-learn), fixture
+    tests/golden/eval_metrics.npz: MCC / P / R / acc / F1 at each of the 101 thresholds, metrics at 0.5, confusion."""
+    from oracle import metrics_oracle as mo
+    g = parity.golden("eval_metrics")
+    for seed in (0, 1):
+        probs, labels = g[f"probs_s{seed}"], g[f"labels_s{seed}"]
+        logits, labels2 = mo.synthetic_scores(len(labels), seed=seed)
+        assert np.array_equal(labels, labels2)
+        np.testing.assert_array_equal(torch.from_numpy(logits).softmax(-1).numpy(), probs)
+        th, counts = mo.thresholded(probs[:, 1], labels)
+        for k in ("mcc", "precision", "recall", "acc", "f1"):
+            np.testing.assert_allclose(th[k], g[f"{k}_s{seed}"], atol=1e-12, rtol=0)
+        i50 = 50  # THRESHOLDS[50] = 0.5
+        # the reference's fourth return value is NOT F1@0.5: its threshold loop reuses the name `f1_val`
+        # (anaysis/metrics.py:196), so what comes back is F1 at the last threshold (1.0)
+        np.testing.assert_allclose([th["acc"][i50], th["precision"][i50], th["recall"][i50], th["f1"][-1]],
+                                   g[f"at05_s{seed}"], atol=1e-12)
+        tn, fp, fn, tp = counts[i50]
+        assert [[tn, fp], [fn, tp]] == g[f"confmat_s{seed}"].tolist()
+        # the binned (101-threshold) AUROC / AP of torchmetrics approximate scikit-learn's exact ones
+        b = mo.torchmetrics_binned(probs[:, 1], labels)
+        sk_auroc, sk_ap = g[f"sk_auroc_ap_s{seed}"]
+        assert abs(b["auroc"] - sk_auroc) < 5e-3 and abs(b["ap"] - sk_ap) < 2e-2
+        # fixture is informative: exact-threshold probabilities are present
+        assert (probs[:, 1] == 0.5).any() and (probs[:, 1] == 1.0).any() and (probs[:, 1] == 0.0).any()
+
+
 def test_sinusoid_table_matches_reference_formula():
     """mf:195-205 evaluated literally (python loops) on a small table."""
     n, d = 7, 10
