@@ -65,3 +65,45 @@ def test_gather_scores_world_size_2_gloo(tmp_path, n_total):
     for r in range(world):
         got = torch.load(os.path.join(str(tmp_path), f"r{r}.pt"))
         assert torch.equal(got, want), f"rank {r} gathered a different score table"
+
+
+def _metrics_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    from oracle import metrics_oracle as mo
+    from simple_tad_b200 import metrics as M
+    from simple_tad_b200.runner import shard_range
+    logits, labels = mo.synthetic_scores(1001, seed=9)
+    probs = torch.from_numpy(logits).softmax(-1).numpy()
+    lo, hi, _ = shard_range(len(labels), world, rank)
+    thr32 = np.asarray(M.THRESHOLDS, dtype=np.float64).astype(np.float32)
+    # this rank's shard of the histogram (what stad_eval_hist returns on the device)
+    bins = np.searchsorted(thr32, probs[lo:hi, 1], side="right")
+    hist = np.zeros((2, 102), dtype=np.int64)
+    np.add.at(hist, (labels[lo:hi], bins), 1)
+    pred = probs[lo:hi, 1] > probs[lo:hi, 0]
+    y = labels[lo:hi].astype(bool)
+    conf = np.array([(~pred & ~y).sum(), (pred & ~y).sum(), (~pred & y).sum(), (pred & y).sum()], dtype=np.int64)
+    h, c = M.reduce_counts(torch.from_numpy(hist), torch.from_numpy(conf))
+    torch.save((h, c), os.path.join(tmp, f"m{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_metric_count_tables_all_reduce_world_size_2_gloo(tmp_path):
+    """Each rank reduces its shard, the ranks sum the count tables: every rank ends with the whole-set metrics."""
+    import numpy as np
+    from oracle import metrics_oracle as mo
+    from simple_tad_b200 import metrics as M
+    world = 2
+    mp.spawn(_metrics_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    logits, labels = mo.synthetic_scores(1001, seed=9)
+    probs = torch.from_numpy(logits).softmax(-1).numpy()
+    th, counts = mo.thresholded(probs[:, 1], labels, np.asarray(M.THRESHOLDS).astype(np.float32))
+    for r in range(world):
+        h, c = torch.load(os.path.join(str(tmp_path), f"m{r}.pt"))
+        got = M.counts_from_hist(h.numpy())
+        assert np.array_equal(got["tp"], counts[:, 3]) and np.array_equal(got["tn"], counts[:, 0])
+        assert M.argmax_metrics(c.numpy())["confmat"] == mo.argmax_metrics(probs, labels)["confmat"]
