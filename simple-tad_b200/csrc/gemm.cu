@@ -14,6 +14,8 @@
 // 32-byte rows (SWIZZLE_32B, so the box is dense); four such boxes make one 64-wide k chunk.
 //
 // Roofline: dense BF16 tensor. Algorithmic FLOPs = 2 M N K; HBM bytes = 2 (M K + N K + M N) (+ 2 M N residual).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -29,12 +31,16 @@ constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kSubCols = 32;                      // columns per epilogue sub-tile = one tcgen05.ld.x32 = one TMA store
 constexpr int kSubTileBytes = BM * kSubCols * 2;  // 8 KB: 128 rows x 64 B, SWIZZLE_64B
 
-template <int BN>
+// kPair: the tile is 256 x BN, computed by the two CTAs of a cluster (one TPC) with tcgen05.mma.cta_group::2.  Each CTA
+// stages its own 128 A rows and HALF of the B rows (the MMA reads the other half from the peer's shared memory), so
+// per flop a CTA moves 2/3 of the operand bytes of the single-CTA tile through L2 -> smem -> tensor core.
+template <int BN, bool kPair = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = kPair ? BN / 2 : BN;   // B rows staged by this CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : BN == 192 ? 4 : BN == 128 ? 6 : 8;
+  static constexpr int STAGES = kPair ? 6 : BN == 256 ? 4 : BN == 192 ? 4 : BN == 128 ? 6 : 8;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int BAR_BYTES = 256;
@@ -83,11 +89,17 @@ STAD_DEVICE TileRows tile_rows(const KArgs& p, int m_tile) {
   return t;
 }
 
-template <int BN, int EPI, bool kPatch>
+template <int BN, int EPI, bool kPatch, bool kPair = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res, const KArgs p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, kPair>;
+  static_assert(!(kPair && kPatch), "the CTA-pair tile is not combined with the patch-embed A operand");
+  // Pair mode: work item = (pair of consecutive M-tiles, n_tile); CTA rank r of the pair owns M-tile 2 * m_pair + r.
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int worker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_workers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned tiles; align in the shared address space.
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -105,8 +117,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   // single-lane TMA / tcgen05.mma issue below takes its operands straight from uniform registers
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_tiles = (kPair ? p.m_tiles / 2 : p.m_tiles) * p.n_tiles;
   const int num_kb = p.K / BK;
+  auto m_tile_of = [&](int tile) { return kPair ? 2 * (tile / p.n_tiles) + static_cast<int>(cta_rank) : tile / p.n_tiles; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -120,16 +133,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], kEpiWarps);
+      // pair: the leader's barrier collects the epilogue warps of BOTH CTAs before an accumulator stage is reused
+      mbar_init(&tmem_empty_bar[s], kPair ? 2 * kEpiWarps : kEpiWarps);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc<C::TMEM_COLS>(tmem_slot);
-    tmem_relinquish();
+    if constexpr (kPair) {
+      tmem_alloc_pair<C::TMEM_COLS>(tmem_slot);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc<C::TMEM_COLS>(tmem_slot);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the peer's barriers exist before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -138,8 +158,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // The whole warp runs the (warp-uniform) loop and the waits; one elected lane issues the copies.
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles;
+    for (int tile = worker; tile < num_tiles; tile += n_workers) {
+      const int m_tile = m_tile_of(tile);
       const int n_tile = tile % p.n_tiles;
       int a_bytes = C::A_BYTES;
       int pe_b = 0, pe_tp = 0, pe_h0 = 0;
@@ -156,6 +176,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (elect_one()) {
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
+          if constexpr (kPair) {
+            // both CTAs' copies are credited to the LEADER's barrier: it expects the bytes of the whole 256-row stage
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (C::A_BYTES + C::B_BYTES));
+            tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, m_tile * BM);
+            tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * BK, n_tile * BN + static_cast<int>(cta_rank) * C::B_ROWS);
+          } else {
           mbar_arrive_expect_tx(&full_bar[stage], a_bytes + C::B_BYTES);
           if constexpr (kPatch) {
             // k chunk kb = 64 consecutive k = (c, dt, dh0..dh0+3, dw 0..15)
@@ -173,6 +199,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_tile * BM);
           }
           tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_tile * BN);
+          }
         }
         __syncwarp();
         if (++stage == C::STAGES) {
@@ -181,14 +208,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && (!kPair || leader)) {
+    // ------------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only)
     // Whole warp in the loop (waits, bookkeeping); one elected lane issues tcgen05.mma / tcgen05.commit.
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(kPair ? 2 * BM : BM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = worker; tile < num_tiles; tile += n_workers, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -212,11 +239,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-              umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              if constexpr (kPair) umma_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              else umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             }
           }
+          if constexpr (kPair) {
+            umma_commit_pair(&empty_bar[stage]);  // frees the stage in BOTH CTAs
+            if (kb == num_kb - 1) umma_commit_pair(&tmem_full_bar[acc]);  // both CTAs' epilogues
+          } else {
           umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
           if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++stage == C::STAGES) {
@@ -225,7 +258,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ------------------------------------------------------------------ epilogue warps
     const int ew = warp - 2;       // 0..7
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
@@ -242,9 +275,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
     // Sub-tile coordinates of running chunk index `ci` of this CTA/warpgroup (tile-major, then column chunk).
     auto chunk_coords = [&](int ci, int& col, int& row0) -> bool {
-      const int tile = blockIdx.x + (ci / CHUNKS) * gridDim.x;
+      const int tile = worker + (ci / CHUNKS) * n_workers;
       if (tile >= num_tiles) return false;
-      const int m_tile = tile / p.n_tiles;
+      const int m_tile = m_tile_of(tile);
       const int n_tile = tile % p.n_tiles;
       col = n_tile * BN + wg * COLS + (ci % CHUNKS) * kSubCols;
       row0 = tile_rows<kPatch>(p, m_tile).row0;
@@ -271,8 +304,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       __syncwarp();
     }
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      const int m_tile = tile / p.n_tiles;
+    for (int tile = worker; tile < num_tiles; tile += n_workers, ++local) {
+      const int m_tile = m_tile_of(tile);
       const int n_tile = tile % p.n_tiles;
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -311,10 +344,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (c + 1 < CHUNKS) {
           tmem_ld32(taddr + (c + 1) * kSubCols, v);  // next chunk streams in under this chunk's math
         } else {
-          // accumulator stage fully in registers: hand it back to the MMA issuer
+          // accumulator stage fully in registers: hand it back to the MMA issuer (pair mode: in the leader CTA)
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) {
+            if constexpr (kPair) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
         }
         const int n0 = n_tile * BN + wg * COLS + c * kSubCols;
         if constexpr (EPI & EPI_LN) {
@@ -418,10 +454,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // neither CTA frees TMEM / exits while the peer's MMAs or arrivals are in flight
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if constexpr (kPair) tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -442,6 +480,55 @@ int set_smem() {
   STAD_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, kPatch>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg<BN>::SMEM_BYTES));
   return STAD_OK;
+}
+
+// CTA-pair variant (256 x 256 tiles, cta_group::2): launched as clusters of two CTAs, one pair per TPC.
+template <int EPI>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                const KArgs& ka, cudaStream_t stream) {
+  using C = Cfg<256, true>;
+  const int tiles = (ka.m_tiles / 2) * ka.n_tiles;
+  const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ProfScope prof(STAD_K_GEMM, EPI | 64, ka.M, ka.N, ka.K, stream);
+  STAD_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<256, EPI, false, true>, ta, tb, to, tr, ka));
+  STAD_LAUNCH_OK("gemm_kernel (CTA pair)");
+  return STAD_OK;
+}
+
+template <int EPI>
+int set_smem_pair() {
+  STAD_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<256, EPI, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg<256, true>::SMEM_BYTES));
+  return STAD_OK;
+}
+
+// STAD_GEMM_PAIR_MIN_K overrides the K from which the pair tile is used (development).
+int pair_min_k() {
+  static const int k = [] {
+    const char* e = getenv("STAD_GEMM_PAIR_MIN_K");
+    return e ? atoi(e) : 2048;
+  }();
+  return k;
+}
+// STAD_GEMM_PAIR=0 in the environment keeps every GEMM on the single-CTA tile (A/B measurements).
+bool pair_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("STAD_GEMM_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 template <int EPI, bool kPatch>
@@ -492,6 +579,11 @@ int gemm_init() {
   if ((rc = set_smem_all_bn<EPI_POS | EPI_STATS, false>())) return rc;
   if ((rc = set_smem_all_bn<EPI_POS | EPI_STATS, true>())) return rc;
   if ((rc = set_smem_all_bn<EPI_LN | EPI_POS, false>())) return rc;
+  if ((rc = set_smem_pair<0>())) return rc;
+  if ((rc = set_smem_pair<EPI_LN>())) return rc;
+  if ((rc = set_smem_pair<EPI_LN | EPI_GELU>())) return rc;
+  if ((rc = set_smem_pair<EPI_RESID>())) return rc;
+  if ((rc = set_smem_pair<EPI_RESID | EPI_STATS>())) return rc;
   return STAD_OK;
 }
 
@@ -554,10 +646,18 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   }
   const int bn = pick_bn(ka.m_tiles, g.N);
   ka.n_tiles = g.N / bn;
+  // CTA-pair tiles (256 x 256) when the shape allows: full-width column tiles, an even number of M-tiles, at least one
+  // tile per pair, and an epilogue that has a pair instantiation
+  const bool pair_epi = g.epi == 0 || g.epi == EPI_LN || g.epi == (EPI_LN | EPI_GELU) || g.epi == EPI_RESID ||
+                        g.epi == (EPI_RESID | EPI_STATS);
+  // ... and a long K loop: with K = 768 (12 k-blocks per tile) the tile time is set by the epilogue, which the pair does
+  // not shorten (measured, B = 64 ViT-B: fc2 K = 3072 331 -> 308 us; qkv 255 -> 255; proj 118 -> 124; fc1 380 -> 404)
+  const bool pair = pair_enabled() && !g.patch && bn == 256 && ka.m_tiles % 2 == 0 && pair_epi &&
+                    g.K >= pair_min_k() && (ka.m_tiles / 2) * ka.n_tiles >= sm_count() / 2;
   {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
     const uint64_t strides[1] = {(uint64_t)g.K * 2};
-    const uint32_t box[2] = {BK, (uint32_t)bn};
+    const uint32_t box[2] = {BK, (uint32_t)(pair ? bn / 2 : bn)};
     if ((rc = make_tmap_bf16(&tb, g.w, 2, dims, strides, box))) return rc;
   }
 
@@ -576,6 +676,15 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     STAD_CHECK_ARG((g.epi & ~EPI_STATS) == EPI_POS, "gemm: patch mode supports only the pos epilogue");
     if (g.epi & EPI_STATS) return dispatch_bn<EPI_POS | EPI_STATS, true>(bn, ta, tb, to, tr, ka, stream);
     return dispatch_bn<EPI_POS, true>(bn, ta, tb, to, tr, ka, stream);
+  }
+  if (pair) {
+    switch (g.epi) {
+      case 0: return launch_pair<0>(ta, tb, to, tr, ka, stream);
+      case EPI_LN: return launch_pair<EPI_LN>(ta, tb, to, tr, ka, stream);
+      case EPI_LN | EPI_GELU: return launch_pair<EPI_LN | EPI_GELU>(ta, tb, to, tr, ka, stream);
+      case EPI_RESID: return launch_pair<EPI_RESID>(ta, tb, to, tr, ka, stream);
+      case EPI_RESID | EPI_STATS: return launch_pair<EPI_RESID | EPI_STATS>(ta, tb, to, tr, ka, stream);
+    }
   }
   switch (g.epi) {
     case EPI_RESID | EPI_STATS: return dispatch_bn<EPI_RESID | EPI_STATS, false>(bn, ta, tb, to, tr, ka, stream);

@@ -258,7 +258,22 @@ def check_gemm_ln_pos(M=320, N=384, K=768, n_rows=1568, eps=1e-6, seed=48):
     return check_gemm(M, N, K, "ln", seed=seed)
 
 
+def check_gemm_pair():
+    """CTA-pair (cta_group::2, 256 x 256) tiles: every epilogue that has a pair instantiation, on shapes the dispatcher
+    sends there (K >= 2048, even number of M-tiles, >= 74 pair tiles), incl. a ragged last M-tile pair and several
+    tiles per pair (persistent loop, accumulator double-buffering across the two CTAs)."""
+    out = []
+    for M, N, K, mode in ((9472, 512, 2048, "plain"), (9472, 512, 2048, "bias"), (9472, 768, 3072, "resid"),
+                          (9472, 512, 2048, "ln"), (9472, 1024, 2048, "ln_gelu"), (25088, 768, 3072, "resid"),
+                          (9472 - 70, 512, 2048, "ln"), (18944, 1024, 2048, "ln_gelu"), (9472, 512, 4096, "resid")):
+        out.append(check_gemm(M, N, K, mode, seed=60 + len(out)))
+    out.append(check_gemm_stats(9472, 768, 512, 3072, seed=7))      # first GEMM: resid + stats on the pair tile
+    out.append(check_gemm_stats(25088 - 128 - 5, 1024, 256, 4096, seed=8))
+    return out
+
+
 CHECKS = {
+    "gemm_pair": check_gemm_pair,
     "decoder_assemble": lambda: [check_decoder_assemble(), check_decoder_assemble(2, 1568, 392, 192, seed=50),
                                  check_decoder_assemble(1, 1568, 160, 512, seed=51)],
     "tail_rows": lambda: [check_tail_rows(), check_tail_rows(2, 1568, 1408, 1536)],
