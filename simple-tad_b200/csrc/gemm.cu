@@ -30,6 +30,8 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kSubCols = 32;                      // columns per epilogue sub-tile = one tcgen05.ld.x32 = one TMA store
 constexpr int kSubTileBytes = BM * kSubCols * 2;  // 8 KB: 128 rows x 64 B, SWIZZLE_64B
+constexpr int kWarpSlots = 4;                      // pair tile: staging slots per epilogue warp
+constexpr int kWarpSlotBytes = 32 * kSubCols * 2;  // 2 KB: the 32 rows of one warp x 64 B
 
 // kPair: the tile is 256 x BN, computed by the two CTAs of a cluster (one TPC) with tcgen05.mma.cta_group::2.  Each CTA
 // stages its own 128 A rows and HALF of the B rows (the MMA reads the other half from the peer's shared memory), so
@@ -40,11 +42,14 @@ struct Cfg {
   static constexpr int B_ROWS = kPair ? BN / 2 : BN;   // B rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = kPair ? 6 : BN == 256 ? 4 : BN == 192 ? 4 : BN == 128 ? 6 : 8;
+  static constexpr int STAGES = kPair ? 5 : BN == 256 ? 4 : BN == 192 ? 4 : BN == 128 ? 6 : 8;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int STAGING_BYTES = 2 * 2 * kSubTileBytes;  // 2 warpgroups x 2 buffers x (128 rows x 64 B)
+  static constexpr int BAR_BYTES = kPair ? 512 : 256;
+  // single-CTA tile: 2 warpgroups x 2 buffers x (128 rows x 64 B), stored by the warpgroup's lead warp;
+  // pair tile: every epilogue warp owns a ring of kWarpSlots (32 rows x 64 B) slots and issues its own TMA stores
+  static constexpr int READY_BARS = kPair ? kEpiWarps * kWarpSlots : 4;
+  static constexpr int STAGING_BYTES = kPair ? kEpiWarps * kWarpSlots * kWarpSlotBytes : 2 * 2 * kSubTileBytes;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of one CTA");
 };
@@ -111,7 +116,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tmem_full_bar = empty_bar + C::STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* buf_ready_bar = tmem_empty_bar + 2;  // [warpgroup][buffer]: staging buffer free (+ residual landed)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_ready_bar + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_ready_bar + C::READY_BARS);
 
   // warp index through a shuffle: the compiler then knows every value derived from it is warp-uniform, and the
   // single-lane TMA / tcgen05.mma issue below takes its operands straight from uniform registers
@@ -126,7 +131,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_out);
     if constexpr (EPI & EPI_RESID) tma_prefetch_desc(&tmap_res);
-    for (int s = 0; s < 4; ++s) mbar_init(&buf_ready_bar[s], 1);
+    for (int s = 0; s < C::READY_BARS; ++s) mbar_init(&buf_ready_bar[s], 1);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -267,11 +272,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     constexpr int CHUNKS = COLS / kSubCols;
     const bool lead_warp = (ew & 3) == 0;            // its elected lane issues the TMA traffic of this warpgroup
     const int r = quarter * 32 + lane;               // accumulator row (TMEM lane) of this thread
-    uint8_t* stage_buf = staging + wg * 2 * kSubTileBytes;
-    uint64_t* ready = buf_ready_bar + wg * 2;
+    uint8_t* stage_buf = kPair ? staging + ew * kWarpSlots * kWarpSlotBytes : staging + wg * 2 * kSubTileBytes;
+    uint64_t* ready = kPair ? buf_ready_bar + ew * kWarpSlots : buf_ready_bar + wg * 2;
     // 64-byte swizzle of the staging tile: 16-byte chunk c of row r lives at chunk position c ^ ((r >> 1) & 3)
-    const uint32_t row_off = static_cast<uint32_t>(r) * 64u;
-    const uint32_t swz = (static_cast<uint32_t>(r) >> 1) & 3u;
+    // (pair tile: rows are counted within the warp's own 32-row slot)
+    const uint32_t srow = kPair ? static_cast<uint32_t>(lane) : static_cast<uint32_t>(r);
+    const uint32_t row_off = srow * 64u;
+    const uint32_t swz = (srow >> 1) & 3u;
 
     // Sub-tile coordinates of running chunk index `ci` of this CTA/warpgroup (tile-major, then column chunk).
     auto chunk_coords = [&](int ci, int& col, int& row0) -> bool {
@@ -280,8 +287,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int m_tile = m_tile_of(tile);
       const int n_tile = tile % p.n_tiles;
       col = n_tile * BN + wg * COLS + (ci % CHUNKS) * kSubCols;
-      row0 = tile_rows<kPatch>(p, m_tile).row0;
+      row0 = tile_rows<kPatch>(p, m_tile).row0 + (kPair ? quarter * 32 : 0);
       return true;
+    };
+    // Pair tile: residual sub-tile (this warp's 32 rows x 32 columns) of running chunk `ci` -> slot ci % kWarpSlots.
+    // The caller has made sure the TMA store that last used the slot has finished reading it.
+    auto prefetch_residual = [&](int ci) {
+      if constexpr (kPair && (EPI & EPI_RESID)) {
+        int col, row0;
+        if (!chunk_coords(ci, col, row0)) return;
+        uint64_t* bar = &ready[ci & (kWarpSlots - 1)];
+        mbar_arrive_expect_tx(bar, kWarpSlotBytes);
+        tma_load_2d(stage_buf + (ci & (kWarpSlots - 1)) * kWarpSlotBytes, &tmap_res, bar, col, row0);
+      }
     };
     // Leader: make staging buffer (ci & 1) usable for chunk ci: the TMA store issued from it two chunks ago must have
     // finished READING it; then either start fetching the residual sub-tile into it or just mark it free.
@@ -299,7 +317,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     };
 
     int ci = 0;
-    if (lead_warp) {
+    if constexpr (kPair) {
+      if (elect_one()) {  // residual sub-tiles are requested two chunks ahead of their use
+        prefetch_residual(0);
+        prefetch_residual(1);
+      }
+      __syncwarp();
+    } else if (lead_warp) {
       if (elect_one()) prepare_buffer(0);
       __syncwarp();
     }
@@ -392,9 +416,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
 
+#if defined(STAD_GEMM_DBG) && STAD_GEMM_DBG >= 3
+        { float acc_ = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc_ += f[j];
+          if (acc_ == 123.456f) p.out[0] = __float2bfloat16(acc_); }
+        continue;  // DBG 3: TMEM load + math only
+#endif
         // staging buffer of this chunk is free (and holds the residual sub-tile, if any)
-        uint8_t* buf = stage_buf + (ci & 1) * kSubTileBytes;
-        mbar_wait(&ready[ci & 1], (ci >> 1) & 1);
+        uint8_t* buf;
+        if constexpr (kPair) {
+          // this warp's ring of kWarpSlots (32 rows x 64 B) slots: chunk ci uses slot ci % kWarpSlots
+          const int slot = ci & (kWarpSlots - 1);
+          buf = stage_buf + slot * kWarpSlotBytes;
+          if constexpr (EPI & EPI_RESID) {
+            mbar_wait(&ready[slot], (ci / kWarpSlots) & 1);  // residual landed; its prefetch knew the slot to be free
+          } else {
+            // stores leave in batches of two chunks (see below): slots {0,1} / {2,3} are free once the batch that last
+            // used them, two batches ago, has been read
+            if ((c & 1) == 0) {
+              if (elect_one()) tma_store_wait_read<1>();
+              __syncwarp();
+            }
+          }
+        } else {
+          buf = stage_buf + (ci & 1) * kSubTileBytes;
+          mbar_wait(&ready[ci & 1], (ci >> 1) & 1);
+        }
         uint4* my_row = reinterpret_cast<uint4*>(buf + row_off);
         if constexpr (EPI & EPI_RESID) {
 #pragma unroll
@@ -429,11 +477,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
           }
         }
+        if constexpr (kPair) {
+          // Every warp stores its own 32 x 32 sub-tile.  The proxy fence is executed by the ISSUING lane only, after
+          // the warp barrier that makes the other lanes' shared-memory writes visible to it: executed by all 32 lanes
+          // (the single-CTA path does that before its 128-thread barrier) it costs 35 us of a 242 us qkv GEMM, the
+          // lanes stalling on it while bulk stores are in flight (ordering: writes -> __syncwarp -> fence.proxy.async
+          // -> cp.async.bulk of the same thread; tests/kernel_checks.py::check_gemm_pair fails reliably without it).
+          __syncwarp();
+          if constexpr (EPI & EPI_RESID) {
+            if (elect_one()) {
+              fence_proxy_async_smem();
+              tma_store_2d(&tmap_out, buf, n0, tr.row0 + quarter * 32);
+              tma_store_commit();
+              tma_store_wait_read<2>();   // slot of chunk ci + 2 was last stored from by chunk ci - 2
+              prefetch_residual(ci + 2);
+            }
+          } else if (c & 1) {
+            // Without a residual the stores leave two chunks at a time: fence.proxy.async stalls the issuing lane while
+            // bulk stores of the CTA are still in flight, and half a tile after the previous batch they no longer are.
+            if (elect_one()) {
+              fence_proxy_async_smem();
+              tma_store_2d(&tmap_out, buf - kWarpSlotBytes, n0 - kSubCols, tr.row0 + quarter * 32);
+              tma_store_2d(&tmap_out, buf, n0, tr.row0 + quarter * 32);
+              tma_store_commit();
+            }
+          }
+          __syncwarp();
+          continue;
+        }
         fence_proxy_async_smem();         // generic-proxy writes -> visible to the TMA (async proxy)
         named_bar_sync(1 + wg, 128);      // whole sub-tile staged
         if (lead_warp) {
           if (elect_one()) {  // deterministic: always the same lane, which owns the bulk async-groups
+#if !defined(STAD_GEMM_DBG) || STAD_GEMM_DBG < 1
             tma_store_2d(&tmap_out, buf, n0, tr.row0);  // rows beyond M (or beyond the box) are clipped by the TMA
+#endif
             tma_store_commit();
             prepare_buffer(ci + 1);
           }
@@ -446,7 +524,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           p.stats_out[static_cast<size_t>(n_tile * 2 + wg) * p.M + row] = make_float2(st_sum, st_sq);
       }
     }
-    if (lead_warp) {
+    if (kPair || lead_warp) {
       if (elect_one()) tma_store_wait<0>();  // all output tiles of this CTA are in global memory
       __syncwarp();
     }
@@ -518,7 +596,7 @@ int set_smem_pair() {
 int pair_min_k() {
   static const int k = [] {
     const char* e = getenv("STAD_GEMM_PAIR_MIN_K");
-    return e ? atoi(e) : 2048;
+    return e ? atoi(e) : 0;
   }();
   return k;
 }
@@ -650,8 +728,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   // tile per pair, and an epilogue that has a pair instantiation
   const bool pair_epi = g.epi == 0 || g.epi == EPI_LN || g.epi == (EPI_LN | EPI_GELU) || g.epi == EPI_RESID ||
                         g.epi == (EPI_RESID | EPI_STATS);
-  // ... and a long K loop: with K = 768 (12 k-blocks per tile) the tile time is set by the epilogue, which the pair does
-  // not shorten (measured, B = 64 ViT-B: fc2 K = 3072 331 -> 308 us; qkv 255 -> 255; proj 118 -> 124; fc1 380 -> 404)
+  // (measured, B = 64 ViT-B, single-CTA -> pair tile with the warp-private epilogue: qkv 259 -> 232 us, fc1 387 -> 346,
+  // fc2 337 -> 318, proj 118 -> 118)
   const bool pair = pair_enabled() && !g.patch && bn == 256 && ka.m_tiles % 2 == 0 && pair_epi &&
                     g.K >= pair_min_k() && (ka.m_tiles / 2) * ka.n_tiles >= sm_count() / 2;
   {
@@ -665,7 +743,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     // output (and residual) sub-tiles: 32 columns x out_box_rows rows, 64-byte swizzle
     const uint64_t dims[2] = {(uint64_t)g.N, (uint64_t)g.M};
     const uint64_t strides[1] = {(uint64_t)g.N * 2};
-    const uint32_t box[2] = {kSubCols, (uint32_t)out_box_rows};
+    const uint32_t box[2] = {kSubCols, (uint32_t)(pair ? 32 : out_box_rows)};  // pair tile: one warp's rows per store
     if ((rc = make_tmap_bf16(&to, g.out, 2, dims, strides, box, 64))) return rc;
     tr = to;
     if (g.epi & EPI_RESID)
