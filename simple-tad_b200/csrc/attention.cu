@@ -41,7 +41,14 @@ constexpr int V_STAGES = 4;
 constexpr int TILE_BYTES = BQ * HD * 2;  // 16 KB: every Q / K / V tile
 constexpr int ATT_THREADS = 512;  // warpgroups 0, 1: softmax slots; 2: epilogue; 3: TMA + 2 MMA issuers (+1 idle warp)
 constexpr int LSUM_BYTES = 2 * BQ * 4;  // row sums handed from the softmax warps to the epilogue warps
-constexpr int SMEM_BYTES = (2 + K_STAGES + V_STAGES) * TILE_BYTES + LSUM_BYTES + 512 + 1024;
+// Key-split tail units (see Unit::split): the four partial O rows of a query are combined through this scratch,
+// [key quarter][column][query] fp32 (query fastest: conflict-free for writers and readers)
+constexpr int SPLIT_ROWS = 32;
+constexpr int SPLIT_SCRATCH_BYTES = 4 * HD * SPLIT_ROWS * 4;
+constexpr int SMEM_BYTES = (2 + K_STAGES + V_STAGES) * TILE_BYTES + LSUM_BYTES + 512 + SPLIT_SCRATCH_BYTES + 1024;
+#ifndef STAD_ATT_SPLIT_TAIL
+#define STAD_ATT_SPLIT_TAIL 1
+#endif
 // Warp roles.  The single-thread TMA / MMA issuers sit in the HIGHEST warps: the sub-partition arbiter favours high warp
 // ids, and an issuer that has to queue behind two always-ready softmax warps paces the whole kernel (measured: ~135
 // clk per tcgen05.mma issue and ~350 clk per already-complete mbarrier wait when the issuers were warps 0-2).
@@ -95,8 +102,15 @@ struct AttArgs {
 #define STAD_ATT_STORE_MODE 0
 #endif
 
+// A one-slot unit whose query tile holds at most 32 rows (the ragged end of the sequence: rows 1536..1567 of 1568)
+// would keep ONE warp busy per tile while costing a whole unit's worth of MMAs and latencies (measured: 11 % of the
+// kernel for 2 % of the rows).  It runs "key-split" instead: the 32 queries are replicated into all four 32-row groups
+// of the Q tile, so every TMEM lane quarter holds their scores against all 128 keys of a tile, and the softmax warp of
+// quarter k handles only keys [32k, 32k+32) of each tile with its own running max / sum (its P entries for the other
+// keys stay zero).  The four partial outputs of a query are merged by the epilogue warps.
 struct Unit {
   int b, h, q0, slots;
+  bool split;
 };
 
 STAD_DEVICE Unit decode_unit(int u, int units_per_head, int H, int S) {
@@ -107,11 +121,13 @@ STAD_DEVICE Unit decode_unit(int u, int units_per_head, int H, int S) {
   w.h = bh - w.b * H;
   w.q0 = t * 2 * BQ;
   w.slots = (w.q0 + BQ < S) ? 2 : 1;
+  w.split = STAD_ATT_SPLIT_TAIL && w.slots == 1 && S - w.q0 <= SPLIT_ROWS;
   return w;
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) {
+attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_q32,
+                 const AttArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -133,6 +149,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
   uint64_t* l_ready = o_full + 2;            // [2]  softmax (128 threads) -> epilogue: unit done, row sums in smem
   uint64_t* o_free = l_ready + 2;            // [2]  epilogue (4 warps) -> MMA: O has been read, next unit may overwrite
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  float* split_scratch = reinterpret_cast<float*>(smem_v + V_STAGES * TILE_BYTES + LSUM_BYTES + 512);
 
   // warp index through a shuffle: the compiler then knows every value derived from it is warp-uniform (uniform
   // registers feed tcgen05.mma / TMA directly instead of a per-lane ELECT + R2UR.BROADCAST loop per instruction)
@@ -147,6 +164,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
 
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_q32);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
       mbar_init(&q_free[s], 1);
@@ -203,7 +221,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
         const int col_k = (p.H + w.h) * HD;
         const int col_v = (2 * p.H + w.h) * HD;
         mbar_wait(&q_free[0], (ucnt0 & 1) ^ 1);
-        load_tile(&q_full[0], smem_q, col_q, w.q0, w.b);
+        if (w.split) {
+          // the same 32 query rows into each of the four 32-row groups of the tile (4 KB apart in the swizzled layout)
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&q_full[0], TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tma_load_3d(smem_q + k * (SPLIT_ROWS * HD * 2), &tmap_q32, &q_full[0], col_q, w.q0, w.b);
+          }
+          __syncwarp();
+        } else {
+          load_tile(&q_full[0], smem_q, col_q, w.q0, w.b);
+        }
         ++ucnt0;
         if (w.slots > 1) {
           mbar_wait(&q_free[1], (ucnt1 & 1) ^ 1);
@@ -348,6 +377,59 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
         mbar_wait(&o_full[slot], (gs[slot] - 1) & 1);      // last P V of the unit
         tc_fence_after();
         ++ucs[slot];
+        if (w.split) {
+          // ---- merge the four key-quarter partials of each of the 32 queries:
+          //   out = sum_k 2^(m_k - M) O_k / sum_k 2^(m_k - M) l_k,  M = max_k m_k
+          float mk[4], M = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            mk[k] = lsum_smem[BQ + k * 32 + lane];
+            M = fmaxf(M, mk[k]);
+          }
+          float L = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) L += (mk[k] == -INFINITY ? 0.f : ex2(mk[k] - M)) * lsum_smem[k * 32 + lane];
+          const float wgt = (mk[quarter] == -INFINITY ? 0.f : ex2(mk[quarter] - M)) / L;
+          named_bar_sync(2, 128);  // the previous split unit's combine has finished reading the scratch
+          const uint32_t o_addr = lane_addr + O_COL;
+          float* mine = split_scratch + quarter * (HD * SPLIT_ROWS) + lane;
+#pragma unroll 1
+          for (int q = 0; q < 4; ++q) {  // 16 columns at a time: these warps run with 56 registers
+            uint32_t ov[16];
+            tmem_ld16(o_addr + q * 16, ov);
+            tmem_ld_wait16(ov);
+            if (q == 3) {  // O is in registers: the next unit's first P V may overwrite it
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&o_free[slot]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mine[(q * 16 + i) * SPLIT_ROWS] = __uint_as_float(ov[i]) * wgt;
+          }
+          named_bar_sync(2, 128);  // all four partials are in the scratch
+          // thread (cg = quarter, query = lane): 16 output columns [16 cg, +16) of query q0 + lane
+          const int qrow = w.q0 + lane;
+          if (qrow < p.S) {
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float* src = split_scratch + (quarter * 16 + i) * SPLIT_ROWS + lane;
+              acc[i] = (src[0] + src[HD * SPLIT_ROWS]) + (src[2 * HD * SPLIT_ROWS] + src[3 * HD * SPLIT_ROWS]);
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(w.b) * p.S + qrow) * (p.H * HD) + w.h * HD +
+                                                 quarter * 16);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint4 o;
+              o.x = pack_bf16(acc[8 * i + 0], acc[8 * i + 1]);
+              o.y = pack_bf16(acc[8 * i + 2], acc[8 * i + 3]);
+              o.z = pack_bf16(acc[8 * i + 4], acc[8 * i + 5]);
+              o.w = pack_bf16(acc[8 * i + 6], acc[8 * i + 7]);
+              op[i] = o;
+            }
+          }
+          continue;
+        }
         const int row = w.q0 + slot * BQ + r;
         const bool warp_valid = w.q0 + slot * BQ + quarter * 32 < p.S;
         const float inv = 1.0f / lsum_smem[slot * BQ + r];
@@ -412,6 +494,74 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttArgs p) 
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const Unit w = decode_unit(u, units_per_head, p.H, p.S);
       if (slot >= w.slots) continue;
+      if (w.split) {
+        // ---- key-split tail unit (slot 0 only): lane i of EVERY quarter holds query q0 + i; this warp handles the
+        // keys [32 * quarter, +32) of each K/V tile: one 32-column chunk of S, one 16-column chunk of P.
+        float m_ref = -INFINITY, l_sum = 0.f;
+        const uint32_t my_s = s_addr + quarter * 32;
+        const uint32_t my_p = p_addr + quarter * 16;
+        for (int j = 0; j < n_kv; ++j, ++g) {
+          const int valid = ((j + 1 < n_kv) ? BKV : last_valid) - quarter * 32;  // keys of this tile in my chunk
+          mbar_wait(&s_full[slot], g & 1);
+          tc_fence_after();
+          uint32_t t[32];
+          if (valid > 0) {
+            tmem_ld32(my_s, t);
+            tmem_ld_wait32(t);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[slot]);
+          if (j == 0) {
+            // P entries of my lanes for the OTHER key chunks stay zero for the whole unit (the P buffer is free here:
+            // s_full of the first tile completes after the last P V of the previous unit)
+            uint32_t z[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q != quarter) tmem_st16(p_addr + q * 16, z);
+          }
+          if (valid > 0) {
+            if (valid < 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i >= valid) t[i] = 0xFF800000u;  // -inf
+            }
+            const float mx = c * chunk_max(t);
+            if (j > 0) {
+              mbar_wait(&o_full[slot], (g - 1) & 1);  // P V of the previous tile: P buffer reusable, O stable
+              tc_fence_after();
+            }
+            const bool grow = mx > m_ref + kRescaleThreshold;  // always true on the first tile with keys (m_ref = -inf)
+            if (__any_sync(0xffffffffu, grow)) {
+              const float alpha = (grow && m_ref != -INFINITY) ? ex2(m_ref - mx) : 1.0f;
+              if (grow) {
+                m_ref = mx;
+                l_sum *= alpha;
+              }
+              if (j > 0) rescale_o(alpha);
+            }
+            uint32_t pk[16];
+            float a0 = 0.f, a1 = 0.f;
+            exp_chunk<false>(t, c, -m_ref, a0, a1, pk);
+            l_sum += a0 + a1;
+            tmem_st16(my_p, pk);
+          } else if (j > 0) {
+            // no key of this tile falls into my chunk (ragged last tile): its P V reads none of my P columns beyond
+            // the zeroed ones; just keep the barrier protocol in step
+            mbar_wait(&o_full[slot], (g - 1) & 1);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[slot]);
+        }
+        lsum_smem[r] = l_sum;        // partial sum of (query lane, key quarter)
+        lsum_smem[BQ + r] = m_ref;   // its reference max (-inf: this quarter never saw a key); slot 1's half is idle here
+        mbar_arrive(&l_ready[slot]);
+        continue;
+      }
       const int row0 = w.q0 + slot * BQ;
       const bool warp_valid = row0 + quarter * 32 < p.S;  // warp-uniform: any valid query row in this warp
       float m_ref = 0.f;  // reference max (log2 domain, already scaled)
@@ -685,9 +835,11 @@ int launch_attention(const bf16* qkv, bf16* out, int B, int H, int S, float scal
   const uint64_t dims[3] = {row, (uint64_t)S, (uint64_t)B};
   const uint64_t strides[2] = {row * 2, row * 2 * (uint64_t)S};
   const uint32_t box[3] = {HD, BQ, 1};
-  CUtensorMap tm;
+  CUtensorMap tm, tm32;
   int rc = make_tmap_bf16(&tm, qkv, 3, dims, strides, box);
   if (rc) return rc;
+  const uint32_t box32[3] = {HD, SPLIT_ROWS, 1};  // Q rows of a key-split tail unit, loaded four times
+  if ((rc = make_tmap_bf16(&tm32, qkv, 3, dims, strides, box32))) return rc;
   AttArgs a;
   a.out = out;
   a.B = B;
@@ -699,7 +851,7 @@ int launch_attention(const bf16* qkv, bf16* out, int B, int H, int S, float scal
   STAD_CHECK_ARG(total_units < (1ll << 30), "attention: B*H*tiles = %lld too large", total_units);
   const int grid = total_units < sm_count() ? static_cast<int>(total_units) : sm_count();
   ProfScope prof(STAD_K_ATTENTION, 0, B, H, S, stream);
-  attention_kernel<<<grid, ATT_THREADS, SMEM_BYTES, stream>>>(tm, a);
+  attention_kernel<<<grid, ATT_THREADS, SMEM_BYTES, stream>>>(tm, tm32, a);
   STAD_LAUNCH_OK("attention_kernel");
   return STAD_OK;
 }

@@ -245,6 +245,14 @@ STAD_DEVICE void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 STAD_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait + data dependence on the loaded registers (keeps their consumers behind the wait)
+STAD_DEVICE void tmem_ld_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
 // Same wait, but with the destination registers of the preceding tcgen05.ld as in/out operands: the compiler cannot
 // schedule a use of them above the wait (the wait itself names no registers).
 STAD_DEVICE void tmem_ld_wait32(uint32_t (&v)[32]) {
