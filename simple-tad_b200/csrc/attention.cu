@@ -730,9 +730,55 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
           have_s = next_full;
           ATT_T(5);
         } else {
-          // ---- last K/V tile with fewer than 128 valid keys: chunk loop, S read twice (max pass, exp pass)
+          // ---- last K/V tile with fewer than 128 valid keys
           mbar_wait(&s_full[slot], g & 1);
           tc_fence_after();
+          if (last_chunks == 1) {
+            // at most 32 valid keys (S = 1568: exactly 32): one chunk, kept in registers between the max and the exps;
+            // S is released before the exps so the issuer is not held up
+            uint32_t t[32];
+            tmem_ld32(s_addr, t);
+            tmem_ld_wait32(t);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[slot]);
+            if (last_valid < 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i >= last_valid) t[i] = 0xFF800000u;  // -inf
+            }
+            const float mx = c * chunk_max(t);
+            if (j == 0) {
+              m_ref = mx;
+            } else {
+              mbar_wait(&o_full[slot], (g - 1) & 1);
+              tc_fence_after();
+              const bool grow = mx > m_ref + kRescaleThreshold;
+              if (__any_sync(0xffffffffu, grow)) {
+                const float alpha = grow ? ex2(m_ref - mx) : 1.0f;
+                if (grow) {
+                  m_ref = mx;
+                  l_sum *= alpha;
+                }
+                rescale_o(alpha);
+              }
+            }
+            uint32_t pk[16];
+            float a0 = 0.f, a1 = 0.f;
+            exp_chunk<false>(t, c, -m_ref, a0, a1, pk);
+            tmem_st16(p_addr, pk);
+            l_sum += a0 + a1;
+#if STAD_ATT_STAGGER
+            if (kStaggerNow && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+#endif
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[slot]);
+            have_s = false;
+            continue;
+          }
+          // general case: chunk loop, S read twice (max pass, exp pass)
           float rmax = -INFINITY;
 #pragma unroll 1
           for (int q = 0; q < last_chunks; ++q) {
