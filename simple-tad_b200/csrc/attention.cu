@@ -92,6 +92,10 @@ struct AttArgs {
 #ifndef STAD_ATT_STAGGER
 #define STAD_ATT_STAGGER 2
 #endif
+#ifndef STAD_ATT_STAGGER_AT
+#define STAD_ATT_STAGGER_AT 0  // slot 1 is released once slot 0 has stored this many + 1 chunks of its first P tile (measured,
+                                // S = 1568: no stagger 722 us; after max 728; chunk 0: 670; chunk 1: 689; chunk 2: 698; chunk 3: 709)
+#endif
 #ifndef STAD_ATT_PROBE
 #define STAD_ATT_PROBE 1
 #endif
@@ -619,6 +623,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_free[slot]);  // S_j is in registers: Q K_{j+1}^T may overwrite it
             ATT_T(1);
+#if STAD_ATT_STAGGER && STAD_ATT_STAGGER_AT == -2
+            if (kStaggerNow && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+#endif
             mx = c * max3(m01, chunk_max(sv[2]), chunk_max(sv[3]));
 #else
             tmem_ld32(s_addr + 0, sv[0]);
@@ -659,6 +666,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
             }
           }
           ATT_T(2);
+#if STAD_ATT_STAGGER && STAD_ATT_STAGGER_AT == -1
+          if (kStaggerNow && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+#endif
           // probe the barrier the first P store needs while chunk 0 is computed (the probe's latency is hidden)
           const bool o_probe = !pv_done && STAD_ATT_PROBE && mbar_try_wait(&o_full[slot], (g - 1) & 1);
           const float neg_m = -m_ref;
@@ -675,9 +685,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
             tc_fence_after();
             ATT_T(9);
             tmem_st16(p_addr, pk0);
+#if STAD_ATT_STAGGER && STAD_ATT_STAGGER_AT == 0
+            if (kStaggerNow && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+#endif
             exp_chunk<true>(sv[1], c, neg_m, b0, b1, pk1);
             tmem_st16(p_addr + 16, pk1);
-#if STAD_ATT_STAGGER
+#if STAD_ATT_STAGGER && STAD_ATT_STAGGER_AT == 1
             if (kStaggerNow && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
 #endif
 #else
@@ -693,6 +706,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
             uint32_t pk2[16];
             exp_chunk<true>(sv[2], c, neg_m, a0, a1, pk2);
             tmem_st16(p_addr + 32, pk2);
+#if STAD_ATT_STAGGER && STAD_ATT_STAGGER_AT == 2
+            if (kStaggerNow && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+#endif
           }
           bool s_ok = false;
           if (next_full) s_ok = mbar_try_wait(&s_full[slot], (g + 1) & 1);
@@ -700,6 +716,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
             uint32_t pk3[16];
             exp_chunk<true>(sv[3], c, neg_m, b0, b1, pk3);
             tmem_st16(p_addr + 48, pk3);
+#if STAD_ATT_STAGGER && STAD_ATT_STAGGER_AT == 3
+            if (kStaggerNow && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+#endif
           }
           l_sum += (a0 + a1) + (b0 + b1);
           ATT_T(3);
