@@ -197,6 +197,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // prologue done (own shared memory / TMEM only); see launch_pdl in common.h
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp >= kTmaWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -916,7 +919,7 @@ int launch_attention(const bf16* qkv, bf16* out, int B, int H, int S, float scal
   STAD_CHECK_ARG(total_units < (1ll << 30), "attention: B*H*tiles = %lld too large", total_units);
   const int grid = total_units < sm_count() ? static_cast<int>(total_units) : sm_count();
   ProfScope prof(STAD_K_ATTENTION, 0, B, H, S, stream);
-  attention_kernel<<<grid, ATT_THREADS, SMEM_BYTES, stream>>>(tm, tm32, a);
+  STAD_CUDA_OK(launch_pdl(attention_kernel, dim3(grid), dim3(ATT_THREADS), SMEM_BYTES, stream, 1, tm, tm32, a));
   STAD_LAUNCH_OK("attention_kernel");
   return STAD_OK;
 }

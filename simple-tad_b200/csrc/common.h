@@ -38,6 +38,37 @@ const char* last_error();
 
 int sm_count();  // SMs of the current device (cached)
 
+// Programmatic dependent launch: the kernel may start (prologue: barrier init, TMEM allocation, descriptor prefetch)
+// while the kernel before it in the stream is still draining; it must execute griddepcontrol.wait (pdl_wait() in
+// ptx.cuh) before it touches any global memory.  STAD_PDL=0 in the environment disables the attribute.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              unsigned cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // rank-N bf16 tensor map. dims/strides innermost-first; strides in BYTES for dims 1..rank-1.
 // swizzle_bytes: 128 (default) or 32.  NOTE: TMA pads a box whose inner extent is narrower than the swizzle span up
 // to the span, so the inner box extent must equal the span for a dense shared-memory tile.

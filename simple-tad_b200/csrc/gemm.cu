@@ -157,6 +157,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if constexpr (kPair) cluster_sync_all();  // the peer's barriers exist before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above touched only this kernel's own shared memory / TMEM: under programmatic dependent launch it ran
+  // while the previous kernel was still draining.  From here on global memory is read and written.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -548,7 +552,8 @@ int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& 
   const int tiles = ka.m_tiles * ka.n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   ProfScope prof(STAD_K_GEMM, EPI | (kPatch ? 32 : 0), ka.M, ka.N, ka.K, stream);
-  gemm_kernel<BN, EPI, kPatch><<<grid, kThreads, C::SMEM_BYTES, stream>>>(ta, tb, to, tr, ka);
+  STAD_CUDA_OK(launch_pdl(gemm_kernel<BN, EPI, kPatch, false>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, 1, ta, tb,
+                          to, tr, ka));
   STAD_LAUNCH_OK("gemm_kernel");
   return STAD_OK;
 }
@@ -567,20 +572,9 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   using C = Cfg<256, true>;
   const int tiles = (ka.m_tiles / 2) * ka.n_tiles;
   const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   ProfScope prof(STAD_K_GEMM, EPI | 64, ka.M, ka.N, ka.K, stream);
-  STAD_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<256, EPI, false, true>, ta, tb, to, tr, ka));
+  STAD_CUDA_OK(launch_pdl(gemm_kernel<256, EPI, false, true>, dim3(2 * pairs), dim3(kThreads), C::SMEM_BYTES, stream, 2, ta,
+                          tb, to, tr, ka));
   STAD_LAUNCH_OK("gemm_kernel (CTA pair)");
   return STAD_OK;
 }

@@ -1,6 +1,7 @@
 // Host-side utilities of libstad.so: thread-local error message, device query, TMA descriptor encoding.
 #include <cudaTypedefs.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <vector>
@@ -106,6 +107,14 @@ int fail(int code, const char* fmt, ...) {
 }
 
 const char* last_error() { return g_err; }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("STAD_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 int sm_count() {
   if (g_sm_count == 0) {

@@ -69,6 +69,13 @@ STAD_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// pdl_wait: block until the kernel before this one in the stream has completed and its writes are visible (no-op when
+// the kernel was not launched with the programmatic-serialization attribute).  pdl_launch_dependents: let the next
+// kernel in the stream begin its prologue once every CTA of this grid has passed this point (or exited).
+STAD_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+STAD_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 STAD_DEVICE void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

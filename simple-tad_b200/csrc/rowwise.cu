@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(256)
 stats_finalize_kernel(const float2* __restrict__ parts, int n_parts, float2* __restrict__ stats, int M, float inv_d,
                       float eps) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();  // launched as a programmatic dependent of the GEMM that wrote `parts`
   if (row >= M) return;
   float s1 = 0.f, s2 = 0.f;
   for (int i = 0; i < n_parts; ++i) {
@@ -454,7 +455,8 @@ int launch_stats_finalize(const float2* parts, int n_parts, float2* stats, int M
   if ((reinterpret_cast<uintptr_t>(parts) | reinterpret_cast<uintptr_t>(stats)) & 7)
     return fail(STAD_E_ALIGN, "stats_finalize: buffers must be 8-byte aligned");
   ProfScope prof(STAD_K_ROW_STATS, 1, M, D, n_parts, stream);
-  stats_finalize_kernel<<<ceil_div(M, 256), 256, 0, stream>>>(parts, n_parts, stats, M, 1.0f / static_cast<float>(D), eps);
+  STAD_CUDA_OK(launch_pdl(stats_finalize_kernel, dim3(ceil_div(M, 256)), dim3(256), 0, stream, 1, parts, n_parts, stats, M,
+                          1.0f / static_cast<float>(D), eps));
   STAD_LAUNCH_OK("stats_finalize");
   return STAD_OK;
 }
