@@ -625,16 +625,26 @@ int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   return fail(STAD_E_SHAPE, "gemm: no tile width for N");
 }
 
-// Widest BN that divides N and still yields at least one full wave of tiles; else the narrowest that divides N.
+// Column-tile width: the divisor of N that minimises  rounds x (BN + 64),  rounds = ceil(tiles / SMs) being the number of
+// tile rounds of the persistent grid and 64 columns standing for the fixed cost of a tile (pipeline fill, accumulator
+// hand-over, epilogue tail).  With many tiles per SM this is the widest tile; at small batch it avoids a mostly empty
+// last round (batch 1, fc1: 156 tiles of 256 columns = 2 rounds -> 208 tiles of 192) and too-narrow tiles (proj: 156
+// tiles of 64 = 2 rounds -> 78 tiles of 128 = 1 round).  Ties go to the wider tile.
 int pick_bn(int m_tiles, int N) {
   const int cand[4] = {256, 192, 128, 64};
-  int narrow = 0;
+  int best = 0;
+  long best_cost = 0;
   for (int i = 0; i < 4; ++i) {
     if (N % cand[i] != 0) continue;
-    narrow = cand[i];
-    if (m_tiles * (N / cand[i]) >= sm_count()) return cand[i];
+    const long tiles = static_cast<long>(m_tiles) * (N / cand[i]);
+    const long rounds = (tiles + sm_count() - 1) / sm_count();
+    const long cost = rounds * (cand[i] + 64);
+    if (best == 0 || cost < best_cost) {
+      best = cand[i];
+      best_cost = cost;
+    }
   }
-  return narrow;
+  return best;
 }
 
 }  // namespace
