@@ -8,7 +8,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EPI = {"24, 1": "patch_embed", "1, 0": "qkv", "20, 0": "proj_or_fc2", "3, 0": "fc1", "4, 0": "fc2_last"}
+EPI = {"24, 1": "patch_embed", "1, 0": "qkv", "20, 0": "proj_or_fc2", "3, 0": "fc1", "4, 0": "fc2_last"}  # <256, EPI, patch(, pair)>
 
 
 def main():
@@ -32,7 +32,7 @@ def main():
         name = r[col["Kernel Name"]]
         if "gemm_kernel" not in name:
             continue
-        key = next((v for k, v in EPI.items() if f"<256, {k}>" in name), None)
+        key = next((v for k, v in EPI.items() if f"<256, {k}>" in name or f"<256, {k}, " in name), None)
         if key == "proj_or_fc2":
             key = "proj" if n_resid % 2 == 0 else "fc2"
             n_resid += 1
@@ -46,7 +46,7 @@ def main():
         per.setdefault(key, rd + wr)
     out = {"model": a.model, "batch": a.batch, "dram_bytes_per_launch": per, "algorithmic_bytes_per_launch": alg,
            "launches": detail,
-           "source": "ncu --set full --clock-control none (one launch of each GEMM of a block, cold cache, serialised); "
+           "source": "ncu --set full --clock-control none (one launch of each GEMM of a block, pair tiles, cold cache, serialised); "
                      "writes below the algorithmic figure stay in the 126 MB L2 for the next kernel"}
     path = os.path.join(ROOT, "profiles", "ncu_gemm_dram.json")
     json.dump(out, open(path, "w"), indent=1)
