@@ -115,7 +115,7 @@ class ClockSampler:
 
 def workload_config(model_name, B, world, sample=None):
     """`config` of both arms: the workload BASELINE.json's metric is quoted on (config 2)."""
-    from oracle import synth
+    import synth_data as synth
     D = synth.ARCHS[model_name][0]
     cfg = {"workload": f"{model_name} 16x224^2 frame-level sliding-window inference, {B} stride-1 windows "
                        f"(one {B + 15}-frame DoTA-shaped synthetic video chunk) per step per GPU, 2-class head",
@@ -206,7 +206,7 @@ def main():
     if world > 1:
         dist.barrier()
     from functools import partial
-    from oracle import synth  # synthetic weights/inputs only (no oracle compute on the GPU arm)
+    import synth_data as synth  # synthetic weights / inputs (repo-level module, not part of oracle/)
     from simple_tad_b200 import _lib, modeling_finetune as mf
     from simple_tad_b200.runner import SlidingWindowRunner, gather_scores
 

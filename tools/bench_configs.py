@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from oracle import synth  # noqa: E402  (synthetic weights / inputs only)
+import synth_data as synth  # noqa: E402  (synthetic weights / inputs)
 from simple_tad_b200 import modeling_finetune as mf, modeling_pretrain as mp  # noqa: E402
 from simple_tad_b200.masking_generator import TubeMaskingGenerator, batch_masks  # noqa: E402
 

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from oracle import synth  # noqa: E402  (synthetic weights / videos only)
+import synth_data as synth  # noqa: E402  (synthetic weights / videos)
 from simple_tad_b200 import modeling_finetune as mf  # noqa: E402
 from simple_tad_b200.runner import SlidingWindowRunner  # noqa: E402
 

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from oracle import synth  # noqa: E402  (synthetic weights / inputs only)
+import synth_data as synth  # noqa: E402  (synthetic weights / inputs)
 from simple_tad_b200 import _lib, modeling_finetune as mf  # noqa: E402
 
 EPI = {0: "bias", 1: "ln", 3: "ln+gelu", 4: "resid", 20: "resid+stats", 8: "pos", 40: "patch-embed", 56: "patch-embed+stats", 24: "pos+stats"}
