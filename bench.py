@@ -153,7 +153,7 @@ def cpu_baseline(model_name, clips=2, repeats=2):
                       f"(torch {torch.__version__} CPU, {torch.get_num_threads()} threads)"}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is pure Python and is not
     present on the GPU box, so this times oracle/ (its restatement, checked against the reference's outputs in
     tests/golden).  Rank 0 alone runs it."""
@@ -181,16 +181,33 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
+
+
+class OnlyJsonOnStdout:
+    """Everything written to fd 1 while the bench runs (NCCL's version banner, library chatter) goes to stderr; the
+    driver reads ONE JSON line from stdout, printed through emit()."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
 
 
 def main():
     args = parse_args()
+    out = OnlyJsonOnStdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     if not torch.cuda.is_available():
@@ -361,7 +378,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
 
 
 if __name__ == "__main__":
