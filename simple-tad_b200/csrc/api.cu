@@ -62,6 +62,9 @@ int make_geom(const stad_dims* d, const stad_input* in, int B, PatchGeom* pg) {
   return STAD_OK;
 }
 
+// Up to this many rows the LN-folded GEMMs finish the LayerNorm statistics themselves (see run_blocks)
+constexpr int kFoldStatsMaxRows = 8192;
+
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct Workspace {
@@ -169,6 +172,7 @@ int run_blocks(const stad_block* blocks, const stad_dims* d, float eps, float at
   const int M = B * n_tok;
   const int D = d->dim;
   const int parts_resid = gemm_stat_parts(M, D, false, nullptr);
+  const bool fold_stats = M <= kFoldStatsMaxRows;
   int parts = parts_in;
   int rc;
   for (int l = 0; l < d->depth; ++l) {
@@ -176,13 +180,22 @@ int run_blocks(const stad_block* blocks, const stad_dims* d, float eps, float at
     const bool last = l + 1 == d->depth;
     const bool emit = !last || final_stats;
     // x = x + proj(attn(norm1(x)))                                     (mf:161)
-    if (parts > 0) {
-      if ((rc = launch_stats_finalize(ws.parts, parts, ws.stats, M, D, eps, stream))) return rc;
-      ++*launches;
-    }
+    // LayerNorm statistics from the partial sums of the GEMM that wrote x.  Few rows (small batch, launch-latency
+    // bound): the LN-folded GEMM finishes them in its own epilogue, one launch less per LayerNorm (batch 1: 0.95 ->
+    // 0.89 ms).  Many rows: a 5 us finalize kernel, because the extra loads sit on the critical path of every tile's
+    // epilogue of kernels that are epilogue-bound (batch 64: folding costs 2.7 %).  parts == 0: ws.stats is ready.
     GemmArgs q;
     q.a = ws.x; q.w = static_cast<const bf16*>(blk.w_qkv); q.M = M; q.N = 3 * D; q.K = D;
-    q.epi = EPI_LN; q.bias = blk.b_qkv; q.colsum = blk.cs_qkv; q.stats = ws.stats; q.out = ws.qkv;
+    q.epi = EPI_LN; q.bias = blk.b_qkv; q.colsum = blk.cs_qkv; q.out = ws.qkv; q.ln_eps = eps;
+    if (parts > 0 && fold_stats) {
+      q.stat_parts = ws.parts; q.n_stat_parts = parts;
+    } else {
+      if (parts > 0) {
+        if ((rc = launch_stats_finalize(ws.parts, parts, ws.stats, M, D, eps, stream))) return rc;
+        ++*launches;
+      }
+      q.stats = ws.stats;
+    }
     if ((rc = launch_gemm(q, stream))) return rc;
     if ((rc = launch_attention(ws.qkv, ws.attn, B, d->heads, n_tok, attn_scale, stream))) return rc;
     GemmArgs pr;
@@ -191,17 +204,23 @@ int run_blocks(const stad_block* blocks, const stad_dims* d, float eps, float at
     if ((rc = launch_gemm(pr, stream))) return rc;
     parts = parts_resid;
     // x = x + fc2(gelu(fc1(norm2(x))))                                 (mf:162)
-    if ((rc = launch_stats_finalize(ws.parts, parts, ws.stats, M, D, eps, stream))) return rc;
     GemmArgs f1;
     f1.a = ws.x; f1.w = static_cast<const bf16*>(blk.w_fc1); f1.M = M; f1.N = d->hidden; f1.K = D;
-    f1.epi = EPI_LN | EPI_GELU; f1.bias = blk.b_fc1; f1.colsum = blk.cs_fc1; f1.stats = ws.stats; f1.out = ws.hidden;
+    f1.epi = EPI_LN | EPI_GELU; f1.bias = blk.b_fc1; f1.colsum = blk.cs_fc1; f1.out = ws.hidden; f1.ln_eps = eps;
+    if (fold_stats) {
+      f1.stat_parts = ws.parts; f1.n_stat_parts = parts;
+    } else {
+      if ((rc = launch_stats_finalize(ws.parts, parts, ws.stats, M, D, eps, stream))) return rc;
+      ++*launches;
+      f1.stats = ws.stats;
+    }
     if ((rc = launch_gemm(f1, stream))) return rc;
     GemmArgs f2;
     f2.a = ws.hidden; f2.w = static_cast<const bf16*>(blk.w_fc2); f2.M = M; f2.N = D; f2.K = d->hidden;
     f2.epi = emit ? (EPI_RESID | EPI_STATS) : EPI_RESID; f2.bias = blk.b_fc2; f2.residual = ws.x; f2.out = ws.x;
     f2.stats_out = emit ? ws.parts : nullptr;
     if ((rc = launch_gemm(f2, stream))) return rc;
-    *launches += 6;
+    *launches += 5;
   }
   return STAD_OK;
 }
@@ -473,19 +492,17 @@ int stad_mae_forward(const stad_mae_model* m, const stad_input* in, const int32_
     return rc;
   // ---- x_vis = encoder_to_decoder(norm(x)) + pos_emd_vis              (mp:107, mp:281, mp:287)
   const int Mv = B * n_vis;
-  if ((rc = launch_stats_finalize(ws.enc.parts, gemm_stat_parts(Mv, de->dim, false, nullptr), ws.enc.stats, Mv, de->dim,
-                                  eps, stream)))
-    return rc;
   GemmArgs e;
   e.a = ws.enc.x; e.w = static_cast<const bf16*>(m->w_e2d); e.M = Mv; e.N = dd->dim; e.K = de->dim;
-  e.epi = EPI_LN | EPI_POS; e.bias = m->b_e2d; e.colsum = m->cs_e2d; e.stats = ws.enc.stats; e.out = ws.vis;
+  e.epi = EPI_LN | EPI_POS; e.bias = m->b_e2d; e.colsum = m->cs_e2d; e.out = ws.vis; e.ln_eps = eps;
+  e.stat_parts = ws.enc.parts; e.n_stat_parts = gemm_stat_parts(Mv, de->dim, false, nullptr);
   e.pos = m->pos_dec; e.tok_idx = vis_idx; e.pos_rows = N;
   if ((rc = launch_gemm(e, stream))) return rc;
   // ---- x_full = cat(x_vis, mask_token + pos_emd_mask) + statistics     (mp:283-288)
   if ((rc = launch_decoder_assemble(ws.vis, m->pos_dec, m->mask_token, mask_idx, ws.dec.x, ws.dec.stats, B, N, n_vis,
                                     dd->dim, eps, stream)))
     return rc;
-  launches += 3;
+  launches += 2;
   // ---- decoder blocks over all N tokens                                 (mp:165-171)
   if ((rc = run_blocks(m->dec_blocks, dd, eps, scale, ws.dec, B, N, 0, /*final_stats=*/true, stream, &launches)))
     return rc;
@@ -494,15 +511,13 @@ int stad_mae_forward(const stad_mae_model* m, const stad_input* in, const int32_
   // rows of one clip are contiguous, the masked rows of the batch are not); the masked rows of its bf16 result are
   // then widened to fp32 into `pixels`.
   const int Mf = B * N;
-  if ((rc = launch_stats_finalize(ws.dec.parts, gemm_stat_parts(Mf, dd->dim, false, nullptr), ws.dec.stats, Mf, dd->dim,
-                                  eps, stream)))
-    return rc;
   GemmArgs h;
   h.a = ws.dec.x; h.w = static_cast<const bf16*>(m->w_pix); h.M = Mf; h.N = dd->num_classes; h.K = dd->dim;
-  h.epi = EPI_LN; h.bias = m->b_pix; h.colsum = m->cs_pix; h.stats = ws.dec.stats; h.out = ws.pix;
+  h.epi = EPI_LN; h.bias = m->b_pix; h.colsum = m->cs_pix; h.out = ws.pix; h.ln_eps = eps;
+  h.stat_parts = ws.dec.parts; h.n_stat_parts = gemm_stat_parts(Mf, dd->dim, false, nullptr);
   if ((rc = launch_gemm(h, stream))) return rc;
   if ((rc = launch_tail_rows_f32(ws.pix, pixels, B, N, N - n_vis, dd->num_classes, stream))) return rc;
-  launches += 3;
+  launches += 2;
   return launches;
 }
 

@@ -60,6 +60,9 @@ struct KArgs {
   const float* bias;
   const float* colsum;
   const float2* stats;
+  const float2* stat_parts;  // EPI_LN alternative to `stats`: [n_stat_parts, M] partial (sum, sumsq) of the input rows
+  int n_stat_parts;
+  float ln_inv_d, ln_eps;
   float2* stats_out;
   const bf16* residual;
   const float* pos;
@@ -344,9 +347,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       float mean = 0.f, rstd = 1.f;
       if constexpr (EPI & EPI_LN) {
         if (row_ok) {
-          const float2 st = __ldg(&p.stats[row]);
-          mean = st.x;
-          rstd = st.y;
+          if (p.stat_parts != nullptr) {
+            // LayerNorm statistics straight from the partial sums the producing GEMM emitted: the same index-order
+            // sum and the same arithmetic as stats_finalize_kernel (bit-identical), without that launch
+            float s1 = 0.f, s2 = 0.f;
+            for (int i = 0; i < p.n_stat_parts; ++i) {
+              const float2 v = __ldg(&p.stat_parts[static_cast<size_t>(i) * p.M + row]);
+              s1 += v.x;
+              s2 += v.y;
+            }
+            mean = s1 * p.ln_inv_d;
+            const float var = fmaxf(fmaf(-mean, mean, s2 * p.ln_inv_d), 0.f);
+            rstd = rsqrtf(var + p.ln_eps);
+          } else {
+            const float2 st = __ldg(&p.stats[row]);
+            mean = st.x;
+            rstd = st.y;
+          }
         }
       }
       float st_sum = 0.f, st_sq = 0.f;  // EPI_STATS: running (sum, sumsq) of this thread's part of the row
@@ -682,7 +699,9 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
        reinterpret_cast<uintptr_t>(g.residual) | reinterpret_cast<uintptr_t>(g.bias) |
        reinterpret_cast<uintptr_t>(g.colsum) | reinterpret_cast<uintptr_t>(g.pos)) & 15)
     return fail(STAD_E_ALIGN, "gemm: all operands must be 16-byte aligned");
-  if (g.epi & EPI_LN) STAD_CHECK_ARG(g.stats && g.colsum, "gemm: LN epilogue needs stats and colsum");
+  if (g.epi & EPI_LN)
+    STAD_CHECK_ARG((g.stats || (g.stat_parts && g.n_stat_parts >= 1 && g.n_stat_parts <= kMaxStatParts)) && g.colsum,
+                   "gemm: LN epilogue needs stats (or partial sums) and colsum");
   if (g.epi & EPI_RESID) STAD_CHECK_ARG(g.residual, "gemm: residual epilogue needs a residual");
   if (g.epi & EPI_POS) STAD_CHECK_ARG(g.pos && (g.tok_idx || g.pos_rows > 0), "gemm: pos epilogue needs a table");
   if (g.epi & EPI_STATS) STAD_CHECK_ARG(g.stats_out, "gemm: statistics epilogue needs an output buffer");
@@ -696,6 +715,10 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   ka.bias = g.bias;
   ka.colsum = g.colsum;
   ka.stats = g.stats;
+  ka.stat_parts = g.stats ? nullptr : g.stat_parts;
+  ka.n_stat_parts = g.n_stat_parts;
+  ka.ln_inv_d = 1.0f / static_cast<float>(g.K);
+  ka.ln_eps = g.ln_eps;
   ka.stats_out = g.stats_out;
   ka.residual = g.residual;
   ka.pos = g.pos;

@@ -30,7 +30,10 @@ struct GemmArgs {
   int epi = 0;                       // EPI_* bits
   const float* bias = nullptr;       // [N] or null
   const float* colsum = nullptr;     // [N]   (EPI_LN)
-  const float2* stats = nullptr;     // [M]   (EPI_LN) (mean, rstd)
+  const float2* stats = nullptr;     // [M]   (EPI_LN) (mean, rstd); or, instead:
+  const float2* stat_parts = nullptr;  // [n_stat_parts, M] partial (sum, sumsq) of the rows of `a` over its K columns,
+  int n_stat_parts = 0;                //   as an EPI_STATS launch wrote them: the epilogue finishes the statistics itself
+  float ln_eps = 1e-6f;                //   (LayerNorm eps for the stat_parts form)
   float2* stats_out = nullptr;       // [2 * n_tiles, M] (EPI_STATS) partial (sum, sumsq) of the stored rows
   const bf16* residual = nullptr;    // [M,N] (EPI_RESID)
   const float* pos = nullptr;        // [pos_rows, N] (EPI_POS)
