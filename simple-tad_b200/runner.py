@@ -172,3 +172,71 @@ class SlidingWindowRunner:
             local_labels = torch.zeros(0, dtype=torch.int32, device=self.device)
         res = M.evaluate(local.softmax(-1), local_labels, group=group)
         return res, gather_scores(local, n_total, group)
+
+
+class StreamingScorer:
+    """Frame-by-frame scoring of a live video: the loop of run_inference.py:69-109 (fill a 16-frame window, then for
+    every new frame drop the oldest, append the newest, predict) without shifting or re-uploading the window.
+
+    The normalised bf16 frames live in a device buffer of 2 x T slots; frame n is written to slots n % T and n % T + T,
+    so the last T frames are always one contiguous run [p + 1, p + T] (p = n % T) that the patch-embed kernel reads
+    straight out of the buffer (stad_input STAD_IN_FRAMES).  `push` takes the frame exactly as `cv2.resize` returns it
+    (uint8 [H, W, 3], BGR), uploads 150 KB, normalises it on the device (prepare_image, ri:15-34) and - once T frames
+    have arrived - returns (logits [num_classes], probs [num_classes]) of the window ending at this frame.
+    `use_graphs=True` replays one captured CUDA graph per buffer phase (T graphs, captured lazily): a batch-1 forward is
+    ~60 launches of a few microseconds each."""
+
+    def __init__(self, model, device=None, bgr=True, mean=IMAGENET_MEAN, std=IMAGENET_STD, use_graphs=True):
+        self.model = model.eval()
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        self.T = model.num_frames
+        pe = model.patch_embed
+        self.H, self.W = pe.img_size
+        self.bgr, self.mean, self.std = bool(bgr), tuple(mean), tuple(std)
+        self.frames = torch.zeros(2 * self.T, 3, self.H, self.W, dtype=torch.bfloat16, device=self.device)
+        self._stage = torch.empty(1, self.H, self.W, 3, dtype=torch.uint8, device=self.device)
+        self._pin = torch.empty(1, self.H, self.W, 3, dtype=torch.uint8).pin_memory()
+        self.n = 0
+        self.use_graphs = bool(use_graphs)
+        self._graphs = {}
+
+    def reset(self):
+        self.n = 0
+
+    def _forward(self, start):
+        return self.model.forward_windows(self.frames, start=start, count=1, stride=1)
+
+    @torch.no_grad()
+    def push(self, frame_u8):
+        """One new frame (uint8 [H, W, 3], host or device).  Returns None until T frames have been pushed, then the
+        (logits, probs) of the current window as host tensors of shape [num_classes]."""
+        if frame_u8.dtype != torch.uint8 or tuple(frame_u8.shape) != (self.H, self.W, 3):
+            raise ValueError(f"expected a uint8 frame [{self.H}, {self.W}, 3], got {frame_u8.dtype} {tuple(frame_u8.shape)}")
+        if frame_u8.is_cuda:
+            self._stage[0].copy_(frame_u8)
+        else:
+            self._pin[0].copy_(frame_u8)
+            self._stage.copy_(self._pin, non_blocking=True)
+        p = self.n % self.T
+        for slot in (p, p + self.T):
+            _lib.normalize_frames_u8(self._stage, self.mean, self.std, bgr=self.bgr, out=self.frames[slot:slot + 1])
+        self.n += 1
+        if self.n < self.T:
+            return None
+        start = p + 1 if p + 1 < self.T else 0  # oldest frame of the window: slot p + 1 (slot 0 when p = T - 1)
+        if not self.use_graphs:
+            logits, probs = self._forward(start)
+            return logits[0].cpu(), probs[0].cpu()
+        g = self._graphs.get(start)
+        if g is None:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self._forward(start)  # warm-up off the capture stream (weight packing, workspace)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward(start)
+            g = self._graphs[start] = (graph, out)
+        g[0].replay()
+        return g[1][0][0].cpu(), g[1][1][0].cpu()

@@ -290,6 +290,33 @@ def test_runner_evaluate_videos_matches_metrics_on_the_gathered_scores():
     np.testing.assert_allclose(res["thresholded"]["mcc"], th["mcc"], atol=1e-12)
 
 
+def test_streaming_scorer_matches_the_sliding_windows():
+    """run_inference.py:69-109 shape: frames arrive one by one; from the 16th on every push returns the score of the
+    window ending at that frame, equal to forward_windows over the whole video (same kernels; the batch size changes
+    the tile widths and with them the grouping of the LayerNorm partial sums, so equality is to ~1e-3, far inside the
+    parity tolerance), identical with and without graph replay."""
+    from simple_tad_b200.runner import SlidingWindowRunner, StreamingScorer
+    sd = synth.make_state_dict("vit_small_d2", seed=11)
+    model = parity.build_classifier("vit_small_d2", sd)
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (37, 224, 224, 3), generator=g, dtype=torch.uint8)  # > 2 x 16 frames: the ring wraps twice
+    ref_logits, ref_probs = SlidingWindowRunner(model, batch_windows=8).score_frames_u8(u8, bgr=True)
+    for use_graphs in (False, True):
+        sc = StreamingScorer(model, use_graphs=use_graphs)
+        outs = [sc.push(f) for f in u8]
+        assert all(o is None for o in outs[:15]) and all(o is not None for o in outs[15:])
+        got = torch.stack([o[0] for o in outs[15:]])
+        assert got.shape == ref_logits.shape
+        parity.check_logits(got, ref_logits, f"streaming (graphs={use_graphs}) vs sliding windows")
+        assert torch.allclose(got, ref_logits, atol=5e-3), float((got - ref_logits).abs().max())
+        assert torch.allclose(torch.stack([o[1] for o in outs[15:]]), ref_probs, atol=2e-3)
+        if use_graphs:
+            assert torch.equal(got, eager), "graph replay differs from the eager streaming scores"
+        eager = got
+    with pytest.raises(ValueError):
+        sc.push(torch.zeros(100, 100, 3, dtype=torch.uint8))
+
+
 def test_config5_batch_sweep_consistency():
     """BASELINE config 5 (correctness side of the batch sweep): ViT-B logits for the same clips at batch 1, 2, 8
     all match the reference within tolerance."""
