@@ -145,7 +145,7 @@ STAD_API const char* stad_last_error(void);
 enum {
   STAD_K_CAST = 0, STAD_K_GATHER = 1, STAD_K_GEMM = 2, STAD_K_ATTENTION = 3, STAD_K_ROW_STATS = 4,
   STAD_K_LAYERNORM = 5, STAD_K_POOL = 6, /* ROW_STATS with epi = 1: stad_stats_finalize */
-  STAD_K_ASSEMBLE = 7, STAD_K_TAIL = 8, STAD_K_NORMALIZE = 9, STAD_K_EVAL = 10
+  STAD_K_ASSEMBLE = 7, STAD_K_TAIL = 8, STAD_K_NORMALIZE = 9, STAD_K_EVAL = 10, STAD_K_RESIZE = 11
 };
 typedef struct stad_profile_record {
   int32_t kind;    /* STAD_K_*                                                        */
@@ -256,6 +256,17 @@ STAD_API int stad_mae_forward(const stad_mae_model* model, const stad_input* in,
  * mean / std: HOST float[3] (RGB order).  The output is the frame buffer stad_input (STAD_IN_FRAMES) reads. */
 STAD_API int stad_normalize_frames_u8(const void* frames_u8, void* out_bf16, int F, int H, int W, const float* mean,
                                       const float* std, int bgr, stad_stream_t stream);
+
+/* uint8 HWC frames [F, H_s, W_s, 3] -> uint8 HWC [F, H_d, W_d, 3], bicubic: `cv2.resize(img, (W_d, H_d),
+ * interpolation=cv2.INTER_CUBIC)` of ri:79-80 / dota.py:347-348 in OpenCV's 8-bit fixed-point arithmetic (imgproc
+ * resize.cpp: taps with A = -0.75 in float32 -> 11-bit weights, clamped source taps, int32 passes, (v + 2^21) >> 22).
+ * The tap tables are built by the caller the way resize.cpp builds them (simple_tad_b200.frames.cubic_taps):
+ *   xofs int32[W_d], xw int16[W_d, 4]: source column of the second tap and the four weights; yofs / yw likewise.
+ * Exact integer arithmetic.  (OpenCV's own result varies by 1 LSB with its build: its SIMD vertical pass works in
+ * float32, and pip builds dispatch this resize to Intel IPP; see oracle/resize_oracle.py.) */
+STAD_API int stad_resize_cubic_u8(const void* frames_u8, void* out_u8, int F, int Hs, int Ws, int Hd, int Wd,
+                                  const int32_t* xofs, const int16_t* xw, const int32_t* yofs, const int16_t* yw,
+                                  stad_stream_t stream);
 
 /* ---- evaluation epilogue ------------------------------------------------------------------------------------------ */
 /* Confusion counts of the per-frame risk probability probs[i][1] against T ascending fp32 thresholds

@@ -240,6 +240,30 @@ def gen_eval_metrics(name):
     save(name, **out)
 
 
+def gen_resize(name):
+    """cv2.resize(..., INTER_CUBIC) as the reference's callers invoke it (ri:79-80, dota.py:347-348), OpenCV's own C++
+    path (IPP off), on synthetic uint8 frames; also records how far the default IPP dispatch is from that path."""
+    import cv2
+    from oracle import resize_oracle as ro
+    out = {"cv2_version": np.array(cv2.__version__)}
+    for i, (h, w, dh, dw) in enumerate(((720, 1280, 224, 224), (360, 640, 224, 224), (100, 60, 37, 23))):
+        img = ro.synthetic_frame(h, w, seed=i)
+        ipp = cv2.ipp.useIPP()
+        with_ipp = cv2.resize(img, dsize=(dw, dh), interpolation=cv2.INTER_CUBIC)
+        cv2.ipp.setUseIPP(False)
+        ref = cv2.resize(img, dsize=(dw, dh), interpolation=cv2.INTER_CUBIC)
+        cv2.ipp.setUseIPP(ipp)
+        mine = ro.resize_cubic_u8(img, dh, dw)
+        d = np.abs(ref.astype(int) - mine.astype(int))
+        d_ipp = np.abs(ref.astype(int) - with_ipp.astype(int))
+        print(f"{name}[{h}x{w} -> {dh}x{dw}]: oracle vs cv2 (IPP off) mismatch {(d > 0).mean():.2e} max {d.max()}; "
+              f"cv2 IPP on vs off mismatch {(d_ipp > 0).mean():.2e} max {d_ipp.max()}")
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3
+        out.update({f"shape_{i}": np.array([h, w, dh, dw]), f"cv2_{i}": ref,
+                    f"rates_{i}": np.array([(d > 0).mean(), (d_ipp > 0).mean()])})
+    save(name, **out)
+
+
 def main():
     install_shims()
     torch.set_num_threads(os.cpu_count())
@@ -254,6 +278,7 @@ def main():
         gen_pretrain("small_mae_vits_d2_b2", "vit_small_d2", B=2, seed=14, decoder_depth=2)
         gen_masks("tube_masks")
         gen_eval_metrics("eval_metrics")
+        gen_resize("resize_cubic")
     if on("peaky"):
         gen_classifier("peaky_vits_d2_b2", "vit_small_d2", B=2, seed=13, peaky=3.0)
     # the five BASELINE.json configs

@@ -19,6 +19,7 @@ EXPORTS = (
     "stad_workspace_bytes", "stad_vit_forward", "stad_profile_enable", "stad_profile_read", "stad_stat_parts",
     "stad_gemm_bias_residual_stats", "stad_stats_finalize", "stad_decoder_assemble", "stad_tail_rows_f32",
     "stad_mae_workspace_bytes", "stad_mae_forward", "stad_normalize_frames_u8", "stad_eval_hist",
+    "stad_resize_cubic_u8",
 )
 
 
@@ -60,7 +61,7 @@ class StadProfileRecord(C.Structure):
 
 
 KIND_NAMES = {0: "cast", 1: "gather", 2: "gemm", 3: "attention", 4: "row_stats", 5: "layernorm", 6: "pool",
-              7: "assemble", 8: "tail", 9: "normalize", 10: "eval"}
+              7: "assemble", 8: "tail", 9: "normalize", 10: "eval", 11: "resize"}
 
 _lib = None
 _inited_devices = set()
@@ -104,6 +105,7 @@ def load():
         "stad_normalize_frames_u8": (C.c_int, [vp, vp, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(C.c_float), i32,
                                                vp]),
         "stad_eval_hist": (C.c_int, [vp, vp, C.c_longlong, vp, i32, vp, vp, vp]),
+        "stad_resize_cubic_u8": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)

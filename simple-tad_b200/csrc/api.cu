@@ -527,4 +527,11 @@ int stad_eval_hist(const float* probs, const int32_t* labels, long long n, const
   return launch_eval_hist(probs, labels, n, thresholds, T, hist, conf, as_stream(stream));
 }
 
+int stad_resize_cubic_u8(const void* frames_u8, void* out_u8, int F, int Hs, int Ws, int Hd, int Wd, const int32_t* xofs,
+                         const int16_t* xw, const int32_t* yofs, const int16_t* yw, stad_stream_t stream) {
+  STAD_CHECK_ARG(frames_u8 && out_u8 && xofs && xw && yofs && yw, "resize_cubic_u8: NULL argument");
+  return launch_resize_cubic_u8(static_cast<const uint8_t*>(frames_u8), static_cast<uint8_t*>(out_u8), F, Hs, Ws, Hd, Wd,
+                                xofs, xw, yofs, yw, as_stream(stream));
+}
+
 }  // extern "C"

@@ -73,4 +73,8 @@ int launch_normalize_u8(const uint8_t* in, bf16* out, int F, int H, int W, const
 int launch_eval_hist(const float* probs, const int32_t* labels, long long n, const float* thresholds, int T,
                      unsigned long long* hist, unsigned long long* conf, cudaStream_t stream);
 
+// bicubic uint8 frame resize in OpenCV's fixed-point arithmetic (run_inference.py:79-80, dota.py:347-348)
+int launch_resize_cubic_u8(const uint8_t* in, uint8_t* out, int F, int Hs, int Ws, int Hd, int Wd, const int32_t* xofs,
+                           const int16_t* xw, const int32_t* yofs, const int16_t* yw, cudaStream_t stream);
+
 }  // namespace stad

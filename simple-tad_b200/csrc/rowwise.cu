@@ -423,6 +423,49 @@ eval_hist_kernel(const float* __restrict__ probs, const int32_t* __restrict__ la
   if (threadIdx.x < 4 && cf[threadIdx.x]) atomicAdd(&conf[threadIdx.x], static_cast<unsigned long long>(cf[threadIdx.x]));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Bicubic frame resize, uint8 HWC -> uint8 HWC: cv2.resize(img, (W_d, H_d), interpolation=cv2.INTER_CUBIC) as the
+// reference's callers invoke it (run_inference.py:79-80, dota.py:347-348), in OpenCV's 8-bit fixed-point arithmetic:
+// 11-bit tap weights (tables built on the host exactly as resize.cpp builds them), source taps clamped at the borders,
+// horizontal pass in int32, vertical pass, (v + 2^21) >> 22, saturation.  Integer arithmetic: bit-exact against the
+// oracle.  One thread per destination pixel (3 channels); block = one destination row segment.
+// Bytes: ~3 F H_s W_s read (every source pixel is touched; re-reads hit L1/L2) + 3 F H_d W_d written.
+__global__ void __launch_bounds__(256)
+resize_cubic_u8_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int Hs, int Ws, int Hd, int Wd,
+                       const int32_t* __restrict__ xofs, const int16_t* __restrict__ xw,
+                       const int32_t* __restrict__ yofs, const int16_t* __restrict__ yw) {
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int dy = blockIdx.y;
+  const int f = blockIdx.z;
+  if (dx >= Wd) return;
+  const int sx = __ldg(&xofs[dx]);
+  const int sy = __ldg(&yofs[dy]);
+  int wx[4], wy[4], cx[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    wx[k] = __ldg(&xw[dx * 4 + k]);
+    wy[k] = __ldg(&yw[dy * 4 + k]);
+    cx[k] = min(max(sx - 1 + k, 0), Ws - 1) * 3;
+  }
+  const uint8_t* src = in + static_cast<size_t>(f) * Hs * Ws * 3;
+  int acc[3] = {0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint8_t* row = src + static_cast<size_t>(min(max(sy - 1 + j, 0), Hs - 1)) * Ws * 3;
+    int h[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) h[c] += static_cast<int>(__ldg(row + cx[k] + c)) * wx[k];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += h[c] * wy[j];
+  }
+  uint8_t* dst = out + ((static_cast<size_t>(f) * Hd + dy) * Wd + dx) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) dst[c] = static_cast<uint8_t>(min(max((acc[c] + (1 << 21)) >> 22, 0), 255));
+}
+
 }  // namespace
 
 int launch_cast_f32_bf16(const float* x, bf16* y, size_t n, cudaStream_t stream) {
@@ -585,6 +628,19 @@ int launch_eval_hist(const float* probs, const int32_t* labels, long long n, con
   ProfScope prof(STAD_K_EVAL, 0, static_cast<int>(n >> 10), T, 0, stream);
   eval_hist_kernel<<<static_cast<unsigned>(blocks), threads, smem, stream>>>(probs, labels, n, thresholds, T, hist, conf);
   STAD_LAUNCH_OK("eval_hist");
+  return STAD_OK;
+}
+
+int launch_resize_cubic_u8(const uint8_t* in, uint8_t* out, int F, int Hs, int Ws, int Hd, int Wd, const int32_t* xofs,
+                           const int16_t* xw, const int32_t* yofs, const int16_t* yw, cudaStream_t stream) {
+  STAD_CHECK_ARG(F > 0 && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0 && Hd <= 65535 && F <= 65535,
+                 "resize_cubic: F=%d src %dx%d dst %dx%d", F, Hs, Ws, Hd, Wd);
+  // |acc| <= 255 * (sum |w_x|) * (sum |w_y|) < 255 * 2^12.4 * 2^12.4: fits int32
+  const int threads = Wd < 256 ? ((Wd + 31) / 32) * 32 : 256;
+  ProfScope prof(STAD_K_RESIZE, 0, F, Hd * Wd, Hs * Ws, stream);
+  resize_cubic_u8_kernel<<<dim3(ceil_div(Wd, threads), Hd, F), threads, 0, stream>>>(in, out, Hs, Ws, Hd, Wd, xofs, xw, yofs,
+                                                                                    yw);
+  STAD_LAUNCH_OK("resize_cubic_u8");
   return STAD_OK;
 }
 

@@ -116,6 +116,16 @@ class SlidingWindowRunner:
         if self._norm_frames is None or self._norm_frames.numel() < n:
             self._norm_frames = torch.empty(n, dtype=torch.bfloat16, device=self.device)
         F_, H, W, _ = dev.shape
+        size = tuple(self.model.patch_embed.img_size)
+        if (H, W) != size:
+            # frames as the camera / decoder delivers them (e.g. 720 x 1280): cv2.resize(..., INTER_CUBIC) of ri:79-80 on
+            # the device, in OpenCV's fixed-point arithmetic
+            from . import frames as _frames
+            dev = _frames.resize_cubic_u8(dev, size)
+            H, W = size
+            n = dev.numel()
+            if self._norm_frames is None or self._norm_frames.numel() < n:
+                self._norm_frames = torch.empty(n, dtype=torch.bfloat16, device=self.device)
         planes = _lib.normalize_frames_u8(dev, mean, std, bgr=bgr, out=self._norm_frames[:n].view(F_, 3, H, W))
         logits, probs = self.score_frames_device(planes)
         return logits.cpu(), probs.cpu()
@@ -210,9 +220,14 @@ class StreamingScorer:
     def push(self, frame_u8):
         """One new frame (uint8 [H, W, 3], host or device).  Returns None until T frames have been pushed, then the
         (logits, probs) of the current window as host tensors of shape [num_classes]."""
-        if frame_u8.dtype != torch.uint8 or tuple(frame_u8.shape) != (self.H, self.W, 3):
-            raise ValueError(f"expected a uint8 frame [{self.H}, {self.W}, 3], got {frame_u8.dtype} {tuple(frame_u8.shape)}")
-        if frame_u8.is_cuda:
+        if frame_u8.dtype != torch.uint8 or frame_u8.dim() != 3 or frame_u8.shape[2] != 3:
+            raise ValueError(f"expected a uint8 frame [H, W, 3], got {frame_u8.dtype} {tuple(frame_u8.shape)}")
+        if tuple(frame_u8.shape[:2]) != (self.H, self.W):
+            # full-size frame: upload it as is and do cv2.resize(..., INTER_CUBIC) (ri:91-92) on the device
+            from . import frames as _frames
+            raw = frame_u8 if frame_u8.is_cuda else frame_u8.pin_memory().to(self.device, non_blocking=True)
+            _frames.resize_cubic_u8(raw[None].contiguous(), (self.H, self.W), out=self._stage)
+        elif frame_u8.is_cuda:
             self._stage[0].copy_(frame_u8)
         else:
             self._pin[0].copy_(frame_u8)

@@ -252,6 +252,33 @@ def check_normalize_u8(F_=5, H=224, W=224, bgr=True, seed=46):
     return _stats(out.cpu(), ref, f"normalize_u8[{F_}x{H}x{W},bgr={bgr}]", 1e-3, 4e-3)
 
 
+def check_resize_cubic():
+    """stad_resize_cubic_u8 against the oracle's integer restatement of cv2 INTER_CUBIC (bit-exact) and against the
+    cv2 outputs of the fixture (<= 1 LSB on < 1e-4 of the pixels: OpenCV's float SIMD pass)."""
+    import numpy as np
+    from oracle import resize_oracle as ro
+    from simple_tad_b200 import frames
+    from tests import parity
+    g = parity.golden("resize_cubic")
+    out = []
+    for i in range(3):
+        h, w, dh, dw = (int(v) for v in g[f"shape_{i}"])
+        imgs = np.stack([ro.synthetic_frame(h, w, seed=i), ro.synthetic_frame(h, w, seed=i + 10)])
+        got = frames.resize_cubic_u8(torch.from_numpy(imgs).to(DEV), (dh, dw)).cpu().numpy()
+        for k in range(2):
+            ref = ro.resize_cubic_u8(imgs[k], dh, dw)
+            assert np.array_equal(got[k], ref), f"resize_cubic[{h}x{w}->{dh}x{dw}]: {(got[k] != ref).sum()} pixels differ from the oracle"
+        d = np.abs(got[0].astype(int) - g[f"cv2_{i}"].astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-4
+        out.append({"name": f"resize_cubic[{h}x{w}->{dh}x{dw}]", "vs_cv2_mismatch": float((d > 0).mean())})
+    # upscale and identity sizes, odd sizes
+    for (h, w, dh, dw) in ((50, 70, 224, 224), (224, 224, 224, 224), (33, 17, 5, 9)):
+        img = ro.synthetic_frame(h, w, seed=7)
+        got = frames.resize_cubic_u8(torch.from_numpy(img[None]).to(DEV), (dh, dw)).cpu().numpy()[0]
+        assert np.array_equal(got, ro.resize_cubic_u8(img, dh, dw)), (h, w, dh, dw)
+    return out
+
+
 def check_gemm_ln_pos(M=320, N=384, K=768, n_rows=1568, eps=1e-6, seed=48):
     """encoder_to_decoder with the encoder norm folded in and the gathered decoder position rows added (mp:107,281,287):
     only reachable through stad_mae_forward, so checked there; here the LN-fold + plain GEMM pieces on the same shape."""
@@ -274,6 +301,7 @@ def check_gemm_pair():
 
 CHECKS = {
     "gemm_pair": check_gemm_pair,
+    "resize_cubic": check_resize_cubic,
     "decoder_assemble": lambda: [check_decoder_assemble(), check_decoder_assemble(2, 1568, 392, 192, seed=50),
                                  check_decoder_assemble(1, 1568, 160, 512, seed=51)],
     "tail_rows": lambda: [check_tail_rows(), check_tail_rows(2, 1568, 1408, 1536)],

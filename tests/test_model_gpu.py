@@ -314,7 +314,18 @@ def test_streaming_scorer_matches_the_sliding_windows():
             assert torch.equal(got, eager), "graph replay differs from the eager streaming scores"
         eager = got
     with pytest.raises(ValueError):
-        sc.push(torch.zeros(100, 100, 3, dtype=torch.uint8))
+        sc.push(torch.zeros(100, 100, 4, dtype=torch.uint8))
+    # full-size frames (resize on the device) give the scores of the frames resized by the oracle's cv2 restatement
+    import numpy as np
+    from oracle import resize_oracle as ro
+    big = np.stack([ro.synthetic_frame(360, 640, seed=100 + i) for i in range(17)])
+    small = torch.from_numpy(np.stack([ro.resize_cubic_u8(f, 224, 224) for f in big]))
+    ref2, _ = SlidingWindowRunner(model, batch_windows=2).score_frames_u8(small, bgr=True)
+    got2, _ = SlidingWindowRunner(model, batch_windows=2).score_frames_u8(torch.from_numpy(big), bgr=True)
+    assert torch.equal(got2, ref2), "device resize + scoring differs from scoring the oracle-resized frames"
+    sc2 = StreamingScorer(model, use_graphs=False)
+    outs2 = [sc2.push(torch.from_numpy(f)) for f in big]
+    assert torch.allclose(torch.stack([o[0] for o in outs2[15:]]), ref2, atol=5e-3)
 
 
 def test_config5_batch_sweep_consistency():

@@ -149,6 +149,31 @@ def test_eval_metrics_oracle_matches_reference_metrics_py():
         assert (probs[:, 1] == 0.5).any() and (probs[:, 1] == 1.0).any() and (probs[:, 1] == 0.0).any()
 
 
+def test_resize_oracle_matches_cv2_inter_cubic():
+    """oracle/resize_oracle.py vs cv2.resize(INTER_CUBIC) as ri:79-80 / dota.py:347-348 call it (fixture written with
+    OpenCV's own C++ path; allowance: OpenCV's float32 SIMD vertical pass, 1 LSB on < 1e-4 of the pixels)."""
+    from oracle import resize_oracle as ro
+    g = parity.golden("resize_cubic")
+    for i in range(3):
+        h, w, dh, dw = (int(v) for v in g[f"shape_{i}"])
+        mine = ro.resize_cubic_u8(ro.synthetic_frame(h, w, seed=i), dh, dw)
+        d = np.abs(mine.astype(int) - g[f"cv2_{i}"].astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-4, (i, d.max(), (d > 0).mean())
+        assert mine.min() == 0 and mine.max() == 255     # the fixture saturates at both ends
+    # the default IPP dispatch of pip's OpenCV is itself ~4 % (1 LSB) away from that path: recorded, not asserted on
+    assert 0.0 <= float(g["rates_0"][1]) < 0.1
+
+
+def test_frames_tap_tables_match_the_oracle():
+    from oracle import resize_oracle as ro
+    from simple_tad_b200 import frames
+    for n_dst, n_src in ((224, 1280), (224, 720), (224, 360), (37, 100), (23, 60), (224, 224), (7, 1000)):
+        o1, w1 = ro.cubic_taps(n_dst, n_src)
+        o2, w2 = frames.cubic_taps(n_dst, n_src)
+        assert np.array_equal(o1, o2) and np.array_equal(w1, w2.astype(np.int32)), (n_dst, n_src)
+        assert w2.dtype == np.int16 and (w2.astype(int).sum(1) >= 2046).all() and (w2.astype(int).sum(1) <= 2050).all()
+
+
 def test_sinusoid_table_matches_reference_formula():
     """mf:195-205 evaluated literally (python loops) on a small table."""
     n, d = 7, 10
