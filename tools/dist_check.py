@@ -48,6 +48,23 @@ def main():
         print(f"dist_check ok: world={world} model={a.model} windows={n}: max|dp| sharded vs single-GPU = {dp:.2e}, "
               f"bit-identical rows = {100 * same:.1f}%")
         assert dp <= 1e-2
+    # evaluation epilogue: every rank reduces ITS shard on the device, the ranks all-reduce the 2 x 102 count table
+    gen = torch.Generator().manual_seed(11)
+    labels = [(torch.rand(v.shape[0], generator=gen) < 0.35).long() for v in videos]
+    res, logits2 = runner.evaluate_videos(videos, labels)
+    assert torch.equal(logits2, table)
+    if rank == 0:
+        from simple_tad_b200 import metrics as M
+        import numpy as np
+        win_labels = torch.cat([l[15:] for l in labels]).to(dev)
+        # single-process reference of the same metrics from the gathered table (no process group involved)
+        hist, conf = M._lib.eval_hist(table.softmax(-1).contiguous(), win_labels.to(torch.int32), M.threshold_tensor(dev))
+        c = M.counts_from_hist(hist.cpu().numpy())
+        for k in ("tn", "fp", "fn", "tp"):
+            assert np.array_equal(c[k], res["counts"][k]), f"sharded {k} counts differ from the single-process counts"
+        assert res["confmat"] == M.argmax_metrics(conf.cpu().numpy())["confmat"] and res["n"] == n
+        print(f"dist_check ok: sharded metric counts == single-process counts; auroc {res['auroc']:.4f} ap {res['ap']:.4f} "
+              f"acc {res['acc']:.4f} confmat {res['confmat']}")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
