@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define STAD_ABI_VERSION 3
+#define STAD_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define STAD_API __attribute__((visibility("default")))
@@ -93,6 +93,13 @@ typedef struct stad_block {
   const float* b_fc2;  /* [D] */
 } stad_block;
 
+/* What the classifier returns (VisionTransformer.forward_features mf:323-330, `final_reduction`). */
+enum {
+  STAD_REDUCE_MEAN = 0, /* fc_norm(mean over tokens)  'fc_norm', mf:325-326: every simple-tad script            */
+  STAD_REDUCE_CLS = 1,  /* norm(x)[:, 0]              'cls',     mf:327-328                                      */
+  STAD_REDUCE_NONE = 2  /* norm(x), every token       'none',    mf:329-330: logits / probs / features per token */
+};
+
 typedef struct stad_model {
   stad_dims dims;
   const void* w_patch;      /* [D, C*tubelet*patch*patch] bf16 = Conv3d weight flattened (c,dt,dh,dw)  (mf:181-183) */
@@ -104,6 +111,10 @@ typedef struct stad_model {
   const float* b_head; /* [num_classes] */
   float eps;           /* 1e-6 (mf:342) */
   float attn_scale;    /* head_dim ** -0.5 (mf:67) */
+  int32_t reduction;   /* STAD_REDUCE_* (classifier models; 0 = the fc_norm path)                                  */
+  const float* cls_token; /* [D] fp32 or NULL: class token of the MVD sibling (other_models/MVD/modeling_finetune.py
+                             :364-366), prepended to every clip after the position add (:431-435); each clip then has
+                             n_tok + 1 rows and STAD_REDUCE_MEAN averages the patch tokens only (:447-449)          */
 } stad_model;
 
 /* PretrainVisionTransformer (mp:183-291) after weight preparation: encoder (visible tokens) -> encoder_to_decoder ->
@@ -128,7 +139,8 @@ typedef struct stad_mae_model {
 typedef struct stad_outputs {
   float* logits;   /* [B, num_classes]  head output, mf:334                                   (classifier models) */
   float* probs;    /* [B, num_classes]  softmax(logits), ris:381 / ri:107                     (classifier models) */
-  float* features; /* [B, D]            fc_norm(mean over tokens) = forward_features, mf:326  (classifier models) */
+  float* features; /* [B, D]            forward_features, mf:326 / mf:328                     (classifier models)
+                      STAD_REDUCE_NONE: the three are per token, [B, S, num_classes] / [B, S, D] (mf:330, mf:334)  */
   float* tokens;   /* [B, n_tok, D]     tokens after `norm`, mp:107-108                       (encoder models)    */
 } stad_outputs;
 
@@ -174,6 +186,19 @@ STAD_API int stad_pool_norm_head(const void* x, const float* g, const float* b, 
                         float* logits, float* probs, float* features, float* scratch, int B, int N, int D, int C,
                         float eps, stad_stream_t stream);
 
+/* LayerNorm of selected rows -> head -> softmax: `norm` followed by final_reduction 'cls' (x[:, 0], mf:327-328:
+ * R = B, row_stride = tokens per clip, row_off = 0) or 'none' (every token, mf:329-330: R = B * S, row_stride = 1) and
+ * the head (mf:334).  Row r is x[(r * row_stride + row_off), :D] bf16.  logits / probs [R, C], features [R, D] fp32;
+ * probs and features may be NULL; w_head NULL (then b_head / logits are not read): features only. */
+STAD_API int stad_rows_norm_head(const void* x, const float* g, const float* b, const float* w_head, const float* b_head,
+                        float* logits, float* probs, float* features, int R, long long row_stride, long long row_off,
+                        int D, int C, float eps, stad_stream_t stream);
+
+/* x[B, N + 1, D] bf16 = cat(cls_token[D] fp32, emb[B, N, D] bf16) per clip, and the LayerNorm statistics (mean, rstd)
+ * float[B * (N + 1), 2] of every row of x.   other_models/MVD/modeling_finetune.py:431-435 (use_cls_token). */
+STAD_API int stad_prepend_cls(const void* emb, const float* cls_token, void* x, float* stats, int B, int N, int D, float eps,
+                     stad_stream_t stream);
+
 /* ---- tensor-core kernels (tcgen05 / TMEM / TMA) ---------------------------------------------------------------- */
 /* Tubelet patch embedding: Conv3d(k = s = (tubelet, patch, patch)) as an im2col-free GEMM + pos/bias table add.
  *   PatchEmbed.forward mf:185-191 and the position add mf:312-313 (mp:93-95 for the encoder).
@@ -213,7 +238,8 @@ STAD_API int stad_stats_finalize(const float* stat_parts, int parts, float* stat
 STAD_API int stad_attention(const void* qkv, void* out, int B, int H, int S, float scale, stad_stream_t stream);
 
 /* ---- whole forward ---------------------------------------------------------------------------------------------- */
-/* Bytes of scratch stad_vit_forward needs for a batch of B clips with n_tok tokens each. */
+/* Bytes of scratch stad_vit_forward needs for a batch of B clips with n_tok tokens each (a model with a class token:
+ * pass n_tok + 1). */
 STAD_API size_t stad_workspace_bytes(const stad_dims* dims, int B, int n_tok);
 
 /* VisionTransformer.forward (mf:308-335) / PretrainVisionTransformerEncoder.forward_features (mp:91-108).
@@ -221,6 +247,8 @@ STAD_API size_t stad_workspace_bytes(const stad_dims* dims, int B, int n_tok);
  *   tok_idx given -> int32[B, n_tok] visible-token ids: the masked-encoder path.
  *   dims.num_classes > 0 -> classifier: out->logits required; out->probs / out->features optional.
  *   dims.num_classes == 0 -> encoder: out->tokens required.
+ *   model->reduction selects what the classifier returns; model->cls_token != NULL prepends a class token (tok_idx
+ *   must be NULL then; the workspace must hold n_tok + 1 tokens per clip).
  * Returns the number of kernels launched (>= 0) or a negative error. */
 STAD_API int stad_vit_forward(const stad_model* model, const stad_input* in, const int32_t* tok_idx, int B, int n_tok,
                      const stad_outputs* out, void* workspace, size_t workspace_bytes, stad_stream_t stream);

@@ -264,6 +264,92 @@ def gen_resize(name):
     save(name, **out)
 
 
+# ---- the other forms of the classifier: final_reduction 'cls' / 'none' and the MVD / UMT siblings -------------------------
+# name: (family, arch, B, seed, kwargs of the reference ctor beyond the common ones, clip frames, image size)
+VARIANTS = {
+    "var_mf_cls_vits_d2_b2": ("mf", "vit_small_d2", 2, 21, dict(final_reduction="cls"), 16, 224),
+    "var_mf_none_vits_d2_b2": ("mf", "vit_small_d2", 2, 22, dict(final_reduction="none"), 16, 224),
+    "var_mvd_vits_d2_b2": ("mvd", "vit_small_d2", 2, 23, dict(), 16, 224),
+    "var_mvd_clstok_vits_d2_b2": ("mvd", "vit_small_d2", 2, 24, dict(use_cls_token=True), 16, 224),
+    "var_mvd_clstok_clsred_vits_d2_b2": ("mvd", "vit_small_d2", 2, 25, dict(use_cls_token=True, final_reduction="cls"), 16, 224),
+    "var_umt_t1f8_vitb_d2_b2": ("umt", "vit_base_d2", 2, 26, dict(tubelet_size=1, all_frames=8), 8, 224),
+    "var_umt_t1f16_vits_d2_b1": ("umt", "vit_small_d2", 1, 27, dict(tubelet_size=1, all_frames=16), 16, 224),
+    "var_umt_384_vits_d2_b1": ("umt", "vit_small_d2", 1, 28, dict(tubelet_size=1, all_frames=8, img_size=384), 8, 384),
+    "var_mvd_vitb_b4": ("mvd", "vit_base_patch16_224", 4, 29, dict(), 16, 224),
+}
+
+
+def _ref_module(family):
+    """The unmodified reference module of a family, imported from its file under a private name (the three files share
+    the name modeling_finetune.py)."""
+    import importlib.util
+    rel = {"mf": "modeling_finetune.py", "mvd": "other_models/MVD/modeling_finetune.py",
+           "umt": "other_models/UMT/modeling_finetune.py"}[family]
+    key = "_stad_ref_" + family
+    if key not in sys.modules:
+        spec = importlib.util.spec_from_file_location(key, os.path.join(REF, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[key] = mod
+        spec.loader.exec_module(mod)
+    return sys.modules[key]
+
+
+def variant_setup(name):
+    """(reference-ctor kwargs, state dict, clips, oracle position table) of a VARIANTS entry — shared with the tests."""
+    family, arch, B, seed, extra, frames, img = VARIANTS[name]
+    D, depth, heads = synth.ARCHS[arch]
+    tubelet = extra.get("tubelet_size", 2)
+    red = extra.get("final_reduction", "fc_norm")
+    sd = synth.make_variant_state_dict(arch, seed=seed, tubelet=tubelet, final_reduction=red,
+                                       cls_token=extra.get("use_cls_token", False))
+    x = synth.make_clips(B, seed=seed, frames=frames, img=img)
+    n_tok = (frames // tubelet) * (img // 16) ** 2
+    if family == "mvd":
+        pos = vit_oracle.sincos_3d_table(D, img // 16, frames // tubelet)
+    elif family == "umt":
+        pos = vit_oracle.umt_table(n_tok, D, frames // tubelet)
+    else:
+        pos = vit_oracle.sinusoid_table(n_tok, D)
+    return family, arch, extra, sd, x, pos, red
+
+
+def gen_variant(name):
+    from functools import partial
+    family, arch, extra, sd, x, pos, red = variant_setup(name)
+    D, depth, heads = synth.ARCHS[arch]
+    mod = _ref_module(family)
+    kw = dict(patch_size=16, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
+              norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=2, all_frames=16, tubelet_size=2,
+              use_flash_attn=False, init_scale=1.0, final_reduction="fc_norm")
+    kw.update(extra)
+    model = mod.VisionTransformer(**kw)
+    sd_load = dict(sd)
+    if isinstance(model.pos_embed, torch.nn.Parameter):   # UMT with an interpolated table: the table is a parameter
+        sd_load["pos_embed"] = model.pos_embed.detach().clone()
+    res = model.load_state_dict(sd_load, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    model.eval()
+    t0 = time.time()
+    with torch.no_grad():
+        feat = model.forward_features(x)
+        logits = model(x)
+    ref_pos = model.pos_embed.detach()
+    print(f"{name}: reference {family} {arch} {extra} on {tuple(x.shape)} -> logits {tuple(logits.shape)} in "
+          f"{time.time() - t0:.1f}s; logits.flat[:2]={logits.flatten()[:2].tolist()}")
+    print(f"  position table {tuple(ref_pos.shape)}: oracle vs reference max|d| = {(pos - ref_pos).abs().max():.3e}")
+    o_logits, o_feat = vit_oracle.vit_forward_variant(sd, x, heads, pos, final_reduction=red, mvd=family == "mvd")
+    print(f"  oracle vs reference: max|dlogit| = {(o_logits - logits).abs().max():.3e}, max|dfeat| = "
+          f"{(o_feat - feat).abs().max():.3e}")
+    n_tok = ref_pos.shape[1]
+    tok = torch.tensor([t for t in HID_TOK if t < n_tok] + [n_tok - 1])
+    ch = torch.tensor(HID_CH)
+    feat_s = feat[..., ch] if feat.dim() == 2 else feat[:, ::97][..., ch]
+    save(name, logits=logits.numpy(), probs=logits.softmax(-1).numpy(), feat_samples=feat_s.numpy(),
+         feat_norm=feat.norm(dim=-1).numpy(), pos_samples=ref_pos[0][tok][:, ch].numpy(), pos_tok=tok.numpy(),
+         pos_sum=np.array([ref_pos.double().sum().item(), ref_pos.double().abs().sum().item()]),
+         hid_ch=np.array(HID_CH))
+
+
 def main():
     install_shims()
     torch.set_num_threads(os.cpu_count())
@@ -294,6 +380,9 @@ def main():
         gen_pretrain("c4_mae_vitb_b2", "vit_base_patch16_224", B=2, seed=6, decoder_depth=4)
     if on("c5"):
         gen_classifier("c5_vitb_b8", "vit_base_patch16_224", B=8, seed=5)
+    for name in VARIANTS:
+        if on("variants") or (want and name in want):
+            gen_variant(name)
 
 
 if __name__ == "__main__":

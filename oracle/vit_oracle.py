@@ -25,8 +25,9 @@ def sinusoid_table(n_position, d_hid):
 
 
 def patch_embed(sd, x):
-    """mf:185-191: Conv3d(k = s = (2,16,16)) then flatten(2).transpose(1,2): tokens ordered (t', h', w')."""
-    y = F.conv3d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=(synth.TUBELET, synth.PATCH, synth.PATCH))
+    """mf:185-191: Conv3d(k = s = (tubelet,16,16)) then flatten(2).transpose(1,2): tokens ordered (t', h', w')."""
+    w = sd["patch_embed.proj.weight"]
+    y = F.conv3d(x, w, sd["patch_embed.proj.bias"], stride=(w.shape[2], synth.PATCH, synth.PATCH))
     return y.flatten(2).transpose(1, 2)
 
 
@@ -75,6 +76,69 @@ def vit_forward(sd, x, heads, return_hidden=False):
     pooled = F.layer_norm(h.mean(1), (D,), sd["fc_norm.weight"], sd["fc_norm.bias"], LN_EPS)  # mf:323-326
     logits = F.linear(pooled, sd["head.weight"], sd["head.bias"])     # mf:334
     return (logits, hidden) if return_hidden else logits
+
+
+def _sincos_1d(dim, pos, scale=None):
+    """mvd:102-122 (other_models/MVD/modeling_finetune.py): [M, dim] = sin | cos of pos x 10000^(-k / (dim/2)), float64."""
+    omega = 1.0 / 10000 ** (np.arange(dim // 2, dtype=float) / (dim / 2.0))
+    pos = np.asarray(pos).reshape(-1)
+    if scale is not None:
+        pos = pos * scale
+    ang = pos[:, None] * omega[None, :]
+    return np.concatenate([np.sin(ang), np.cos(ang)], axis=1)
+
+
+def sincos_3d_table(d_hid, grid_size, t_size):
+    """MVD position table, mvd:24-69: per token (t', h', w'): [ 1-D sincos of t' (D/4) | 1-D sincos of w' (3D/8) | 1-D
+    sincos of h' (3D/8) ] — np.meshgrid(w, h) puts the w' coordinate first (mvd:38-39, mvd:92-97).  [1, T*H*W, D] fp32."""
+    d_t, d_s = d_hid // 4, d_hid // 4 * 3
+    ax = np.arange(grid_size, dtype=np.float32)
+    ww = np.tile(ax[None, :], (grid_size, 1)).reshape(-1)    # w' of token (h', w') in row-major order
+    hh = np.tile(ax[:, None], (1, grid_size)).reshape(-1)    # h'
+    spatial = np.concatenate([_sincos_1d(d_s // 2, ww), _sincos_1d(d_s // 2, hh)], axis=1)    # [H*W, 3D/4]
+    temporal = _sincos_1d(d_t, np.arange(t_size, dtype=np.float32))                           # [T, D/4]
+    tab = np.concatenate([np.repeat(temporal[:, None], grid_size ** 2, 1), np.repeat(spatial[None], t_size, 0)], -1)
+    return torch.FloatTensor(tab.reshape(-1, d_hid)).unsqueeze(0)
+
+
+def umt_table(n_position, d_hid, cur_frame, pre_n_position=1568):
+    """UMT position table, umt:195-239 (other_models/UMT/modeling_finetune.py): the 1568-row sinusoid table of the 8 x 14
+    x 14 pre-training grid, bicubic over (h', w') if the image grid differs, linear over t' if the clip length does."""
+    tab = sinusoid_table(pre_n_position, d_hid)
+    if cur_frame != -1 and n_position // cur_frame * 8 != pre_n_position:     # umt:208-221
+        new_p = int((n_position // cur_frame) ** 0.5)
+        t = tab.reshape(8, 14, 14, d_hid).permute(0, 3, 1, 2)
+        t = F.interpolate(t, size=(new_p, new_p), mode="bicubic", align_corners=False)
+        tab = t.permute(0, 2, 3, 1).reshape(1, 8 * new_p * new_p, d_hid)
+    if cur_frame != -1 and cur_frame != 8:                                    # umt:222-234
+        p = int((n_position // cur_frame) ** 0.5)
+        t = tab.reshape(8, p * p, d_hid).permute(1, 2, 0)                     # [HW, C, T]
+        t = F.interpolate(t, size=cur_frame, mode="linear")
+        tab = t.permute(2, 0, 1).reshape(1, cur_frame * p * p, d_hid)
+    return tab
+
+
+@torch.no_grad()
+def vit_forward_variant(sd, x, heads, pos, final_reduction="fc_norm", mvd=False):
+    """The classifier forward in its other forms: any position table `pos` [1, N, D] (mf:312-313), MVD's class token
+    prepended after the position add when `cls_token` is in sd (mvd:428-435), and the three reductions —
+    'fc_norm': fc_norm(mean of the patch tokens) (mf:325-326; mvd:447-449 drops the class token first),
+    'cls': norm(x)[:, 0] (mf:327-328), 'none': norm(x) per token (mf:329-330; MVD returns x[:, 0] here too, mvd:450-451)
+    — followed by the head (mf:334).  Returns (logits, features)."""
+    D = sd["patch_embed.proj.bias"].shape[0]
+    h = patch_embed(sd, x) + pos
+    if "cls_token" in sd:
+        h = torch.cat((sd["cls_token"].expand(h.shape[0], -1, -1), h), dim=1)
+    for i in range(_depth(sd)):
+        h = block(sd, i, h, heads)
+    if final_reduction == "fc_norm":
+        if "cls_token" in sd:
+            h = h[:, 1:]
+        feat = F.layer_norm(h.mean(1), (D,), sd["fc_norm.weight"], sd["fc_norm.bias"], LN_EPS)
+    else:
+        h = F.layer_norm(h, (D,), sd["norm.weight"], sd["norm.bias"], LN_EPS)
+        feat = h[:, 0] if (final_reduction == "cls" or mvd) else h
+    return F.linear(feat, sd["head.weight"], sd["head.bias"]), feat
 
 
 @torch.no_grad()

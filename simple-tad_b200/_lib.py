@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("STAD_LIB") or os.path.join(_HERE, "libstad.so")  # ST
 STAD_OK, STAD_E_SHAPE, STAD_E_ALIGN, STAD_E_ARCH, STAD_E_CUDA = 0, -1, -2, -3, -4
 STAD_EPI_BIAS, STAD_EPI_BIAS_GELU = 0, 1
 STAD_IN_CLIPS, STAD_IN_FRAMES = 0, 1
+STAD_REDUCE_MEAN, STAD_REDUCE_CLS, STAD_REDUCE_NONE = 0, 1, 2
 
 EXPORTS = (
     "stad_abi_version", "stad_init", "stad_last_error", "stad_cast_f32_bf16", "stad_row_stats", "stad_layernorm",
@@ -19,7 +20,7 @@ EXPORTS = (
     "stad_workspace_bytes", "stad_vit_forward", "stad_profile_enable", "stad_profile_read", "stad_stat_parts",
     "stad_gemm_bias_residual_stats", "stad_stats_finalize", "stad_decoder_assemble", "stad_tail_rows_f32",
     "stad_mae_workspace_bytes", "stad_mae_forward", "stad_normalize_frames_u8", "stad_eval_hist",
-    "stad_resize_cubic_u8",
+    "stad_resize_cubic_u8", "stad_rows_norm_head", "stad_prepend_cls",
 )
 
 
@@ -41,7 +42,7 @@ class StadBlock(C.Structure):
 class StadModel(C.Structure):
     _fields_ = [("dims", StadDims), ("w_patch", C.c_void_p), ("pos_bias", C.c_void_p), ("blocks", C.POINTER(StadBlock)),
                 ("norm_g", C.c_void_p), ("norm_b", C.c_void_p), ("w_head", C.c_void_p), ("b_head", C.c_void_p),
-                ("eps", C.c_float), ("attn_scale", C.c_float)]
+                ("eps", C.c_float), ("attn_scale", C.c_float), ("reduction", C.c_int32), ("cls_token", C.c_void_p)]
 
 
 class StadMaeModel(C.Structure):
@@ -106,6 +107,9 @@ def load():
                                                vp]),
         "stad_eval_hist": (C.c_int, [vp, vp, C.c_longlong, vp, i32, vp, vp, vp]),
         "stad_resize_cubic_u8": (C.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+        "stad_rows_norm_head": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, i32, C.c_longlong, C.c_longlong, i32, i32, f32,
+                                          vp]),
+        "stad_prepend_cls": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, f32, vp]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -212,6 +216,41 @@ def pool_norm_head(x, g, b, w_head, b_head, eps, want_probs=False, want_features
                                      stream_ptr()), "stad_pool_norm_head")
     res = (logits,) + ((probs,) if want_probs else ()) + ((feats,) if want_features else ())
     return res if len(res) > 1 else logits
+
+
+def rows_norm_head(x, g, b, w_head, b_head, eps, rows="all", want_probs=False, want_features=False):
+    """x [B, S, D] bf16 -> LayerNorm of token 0 of every clip (rows="cls", mf:327-328) or of every token (rows="all",
+    mf:329-330), then the head (mf:334).  Returns logits (, probs) (, features), leading shape [B] or [B, S]."""
+    init(x.device)
+    _req(x, torch.bfloat16, "x")
+    B, S, D = x.shape
+    lead = (B,) if rows == "cls" else (B, S)
+    R, stride = (B, S) if rows == "cls" else (B * S, 1)
+    Cn = w_head.shape[0]
+    logits = torch.empty(lead + (Cn,), dtype=torch.float32, device=x.device)
+    probs = torch.empty(lead + (Cn,), dtype=torch.float32, device=x.device) if want_probs else None
+    feats = torch.empty(lead + (D,), dtype=torch.float32, device=x.device) if want_features else None
+    check(load().stad_rows_norm_head(ptr(x), ptr(g), ptr(b), ptr(_req(w_head, torch.float32, "w_head")), ptr(b_head),
+                                     ptr(logits), ptr(probs), ptr(feats), R, stride, 0, D, Cn, float(eps), stream_ptr()),
+          "stad_rows_norm_head")
+    res = (logits,) + ((probs,) if want_probs else ()) + ((feats,) if want_features else ())
+    return res if len(res) > 1 else logits
+
+
+def prepend_cls(emb, cls_token, eps):
+    """emb [B, N, D] bf16, cls_token [D] fp32 -> (x [B, N + 1, D] bf16 = cat(cls, emb), stats [B*(N+1), 2] fp32)
+    (other_models/MVD/modeling_finetune.py:431-435)."""
+    init(emb.device)
+    _req(emb, torch.bfloat16, "emb")
+    _req(cls_token, torch.float32, "cls_token")
+    B, N, D = emb.shape
+    if cls_token.numel() != D:
+        raise ValueError(f"prepend_cls: cls_token has {cls_token.numel()} values for D={D}")
+    x = torch.empty(B, N + 1, D, dtype=torch.bfloat16, device=emb.device)
+    stats = torch.empty(B * (N + 1), 2, dtype=torch.float32, device=emb.device)
+    check(load().stad_prepend_cls(ptr(emb), ptr(cls_token), ptr(x), ptr(stats), B, N, D, float(eps), stream_ptr()),
+          "stad_prepend_cls")
+    return x, stats
 
 
 def ln_gemm(x, stats, w, bias, colsum, gelu=False, out=None):

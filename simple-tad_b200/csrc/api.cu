@@ -98,7 +98,8 @@ Workspace carve(const stad_dims* d, int B, int n_tok, void* base) {
   const size_t o_big = take(M * hid * 2);
   const size_t o_pool = take(static_cast<size_t>(B) * 16 * D * sizeof(float));
   const int n_full = (d->frames / d->tubelet) * (d->img_h / 16) * (d->img_w / 16);
-  const size_t o_gather = take(n_tok == n_full ? 0 : M * K * 2);  // im2col scratch only on the visible-token path
+  // im2col scratch only on the visible-token path (n_full + 1 rows: every token plus a class token)
+  const size_t o_gather = take(n_tok == n_full || n_tok == n_full + 1 ? 0 : M * K * 2);
   w.x = reinterpret_cast<bf16*>(p + o_x);
   w.stats = reinterpret_cast<float2*>(p + o_stats);
   w.parts = reinterpret_cast<float2*>(p + o_parts);
@@ -306,6 +307,19 @@ int stad_pool_norm_head(const void* x, const float* g, const float* b, const flo
                                N, D, C, eps, as_stream(stream));
 }
 
+int stad_rows_norm_head(const void* x, const float* g, const float* b, const float* w_head, const float* b_head,
+                        float* logits, float* probs, float* features, int R, long long row_stride, long long row_off,
+                        int D, int C, float eps, stad_stream_t stream) {
+  return launch_rows_norm_head(static_cast<const bf16*>(x), g, b, w_head, b_head, logits, probs, features, R, row_stride,
+                               row_off, D, C, eps, as_stream(stream));
+}
+
+int stad_prepend_cls(const void* emb, const float* cls_token, void* x, float* stats, int B, int N, int D, float eps,
+                     stad_stream_t stream) {
+  return launch_prepend_cls(static_cast<const bf16*>(emb), cls_token, static_cast<bf16*>(x),
+                            reinterpret_cast<float2*>(stats), B, N, D, eps, as_stream(stream));
+}
+
 int stad_patch_embed(const stad_input* in, const void* w, const float* pos_bias, const int32_t* tok_idx, void* out,
                      void* gather, const stad_dims* dims, int B, int n_tok, stad_stream_t stream) {
   int launches = 0;
@@ -396,7 +410,15 @@ int stad_vit_forward(const stad_model* m, const stad_input* in, const int32_t* t
   STAD_CHECK_ARG(d->heads * 64 == d->dim, "vit_forward: head dim must be 64 (dim=%d heads=%d)", d->dim, d->heads);
   STAD_CHECK_ARG(workspace != nullptr, "vit_forward: workspace is NULL");
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(STAD_E_ALIGN, "vit_forward: workspace must be 256-byte aligned");
-  Workspace ws = carve(d, B, n_tok, workspace);
+  const bool with_cls = m->cls_token != nullptr;
+  const int S = n_tok + (with_cls ? 1 : 0);  // rows per clip in the residual stream
+  if (with_cls)
+    STAD_CHECK_ARG(tok_idx == nullptr && n_tok == full_tokens(d),
+                   "vit_forward: a class token needs every patch token (n_tok=%d of %d, no index list)", n_tok,
+                   full_tokens(d));
+  STAD_CHECK_ARG(m->reduction >= STAD_REDUCE_MEAN && m->reduction <= STAD_REDUCE_NONE, "vit_forward: reduction=%d",
+                 m->reduction);
+  Workspace ws = carve(d, B, S, workspace);
   STAD_CHECK_ARG(ws.bytes <= workspace_bytes, "vit_forward: workspace too small (%zu < %zu bytes)", workspace_bytes,
                  ws.bytes);
   const bool classifier = d->num_classes > 0;
@@ -405,26 +427,44 @@ int stad_vit_forward(const stad_model* m, const stad_input* in, const int32_t* t
   STAD_CHECK_ARG(m->norm_g && m->norm_b, "vit_forward: final norm weights missing");
 
   cudaStream_t stream = as_stream(stream_);
-  const int M = B * n_tok;
+  const int M = B * S;
   const int D = d->dim;
   int launches = 0;
 
   // PatchEmbed + position table (mf:309-313 / mp:93-98).  Its epilogue also emits the LayerNorm partial sums of the
   // rows it stores, as does every GEMM below that writes the residual stream: no separate statistics pass.
   int parts = 0;
-  if ((rc = patch_embed_impl(in, m->w_patch, m->pos_bias, tok_idx, ws.x, ws.gather, d, B, n_tok, stream, &launches,
-                             ws.parts, &parts)))
-    return rc;
-  if ((rc = run_blocks(m->blocks, d, m->eps, m->attn_scale, ws, B, n_tok, parts, /*final_stats=*/false, stream,
+  if (!with_cls) {
+    if ((rc = patch_embed_impl(in, m->w_patch, m->pos_bias, tok_idx, ws.x, ws.gather, d, B, n_tok, stream, &launches,
+                               ws.parts, &parts)))
+      return rc;
+  } else {
+    // MVD class token (MVD mf:431-435): the patch rows go to the (still unused) hidden buffer, one row kernel lays
+    // out [cls | patches] per clip in the residual stream and writes the statistics of norm1 of the first block.
+    if ((rc = patch_embed_impl(in, m->w_patch, m->pos_bias, nullptr, ws.hidden, ws.gather, d, B, n_tok, stream,
+                               &launches)))
+      return rc;
+    if ((rc = launch_prepend_cls(ws.hidden, m->cls_token, ws.x, ws.stats, B, n_tok, D, m->eps, stream))) return rc;
+    launches += 1;
+  }
+  if ((rc = run_blocks(m->blocks, d, m->eps, m->attn_scale, ws, B, S, parts, /*final_stats=*/false, stream,
                        &launches)))
     return rc;
 
-  if (classifier) {
-    // norm = Identity; mean over tokens; fc_norm; head                (mf:323-326, mf:334)
-    if ((rc = launch_pool_norm_head(ws.x, m->norm_g, m->norm_b, m->w_head, m->b_head, logits, probs, features, ws.pool,
-                                    B, n_tok, D, d->num_classes, m->eps, stream)))
+  if (classifier && m->reduction == STAD_REDUCE_MEAN) {
+    // norm = Identity; mean over (patch) tokens; fc_norm; head        (mf:323-326, mf:334; MVD mf:447-449)
+    if ((rc = launch_pool_norm_head(ws.x + (with_cls ? D : 0), m->norm_g, m->norm_b, m->w_head, m->b_head, logits, probs,
+                                    features, ws.pool, B, n_tok, D, d->num_classes, m->eps, stream,
+                                    static_cast<size_t>(S) * D)))
       return rc;
     launches += 2;
+  } else if (classifier) {
+    // norm over the rows that are returned; head                      (mf:323, mf:327-330, mf:334)
+    const bool cls_only = m->reduction == STAD_REDUCE_CLS;
+    if ((rc = launch_rows_norm_head(ws.x, m->norm_g, m->norm_b, m->w_head, m->b_head, logits, probs, features,
+                                    cls_only ? B : M, cls_only ? S : 1, 0, D, d->num_classes, m->eps, stream)))
+      return rc;
+    launches += 1;
   } else {
     // encoder: norm over every visible token, head = Identity         (mp:107, mp:112)
     if ((rc = launch_layernorm(ws.x, m->norm_g, m->norm_b, tokens_out, M, D, m->eps, stream))) return rc;

@@ -57,7 +57,14 @@ int launch_layernorm(const bf16* x, const float* g, const float* b, float* y, in
                      cudaStream_t stream);
 int launch_pool_norm_head(const bf16* x, const float* g, const float* b, const float* w_head, const float* b_head,
                           float* logits, float* probs, float* features, float* scratch, int B, int N, int D, int C,
-                          float eps, cudaStream_t stream);
+                          float eps, cudaStream_t stream, size_t clip_stride = 0);  // 0: clips are dense, N * D apart
+// final_reduction 'cls' / 'none': LayerNorm of rows r * row_stride + row_off (r < R) -> features / head / softmax
+int launch_rows_norm_head(const bf16* x, const float* g, const float* b, const float* w_head, const float* b_head,
+                          float* logits, float* probs, float* features, int R, long long row_stride, long long row_off,
+                          int D, int C, float eps, cudaStream_t stream);
+// MVD class token: x[B, N + 1, D] = cat(cls_token, emb[B, N, D]) + (mean, rstd) of every row
+int launch_prepend_cls(const bf16* emb, const float* cls_token, bf16* x, float2* stats, int B, int N, int D, float eps,
+                       cudaStream_t stream);
 // visible-token im2col: out[B*n_tok, K] bf16 rows (c, dt, dh, dw) of the listed tokens
 int launch_gather_patches(const bf16* planes, const PatchGeom& pg, const int32_t* tok_idx, bf16* out, int B,
                           int n_tok, cudaStream_t stream);

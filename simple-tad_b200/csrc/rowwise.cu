@@ -132,12 +132,13 @@ stats_finalize_kernel(const float2* __restrict__ parts, int n_parts, float2* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// mean-pool stage 1: grid (kPoolChunks, B); block sums its slice of the tokens for every column.
+// mean-pool stage 1: grid (kPoolChunks, B); block sums its slice of the tokens for every column.  Clip b starts at
+// x + b * clip_stride elements (N * D, or (N + 1) * D with x advanced by one row when a class token leads every clip).
 // Bytes: 2 B N D read + 4 B kPoolChunks D written.  Deterministic (no atomics).
 constexpr int kPoolChunks = 16;
 
 __global__ void __launch_bounds__(256)
-pool_partial_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int N, int D) {
+pool_partial_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int N, int D, size_t clip_stride) {
   extern __shared__ float red[];  // [groups][D]
   const int cpr = D >> 3;                 // 16-byte chunks per row
   const int groups = blockDim.x / cpr;    // row groups working in parallel
@@ -149,7 +150,7 @@ pool_partial_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int
   const int n1 = min(N, n0 + per);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (grp < groups) {
-    const uint4* base = reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * N * D) + ch;
+    const uint4* base = reinterpret_cast<const uint4*>(x + static_cast<size_t>(b) * clip_stride) + ch;
     for (int n = n0 + grp; n < n1; n += groups) {
       float f[8];
       unpack8(__ldg(base + static_cast<size_t>(n) * cpr), f);
@@ -232,6 +233,154 @@ pool_head_kernel(const float* __restrict__ partial, const float* __restrict__ g,
     for (int c = 0; c < C; ++c) den += expf(lg[c] - mx);
     for (int c = 0; c < C; ++c) probs[static_cast<size_t>(bidx) * C + c] = expf(lg[c] - mx) / den;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// final_reduction 'cls' / 'none' (modeling_finetune.py:323-334): LayerNorm of selected rows of the residual stream,
+// then the head and the softmax.  One warp per selected row r, which is row r * row_stride + row_off of x:
+// 'cls' reads row 0 of every clip (row_stride = tokens per clip), 'none' every row (row_stride = 1).
+// Bytes: 2 R D read + 4 R (D + 2 C) written (features optional).
+__global__ void __launch_bounds__(256)
+rows_norm_head_kernel(const bf16* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                      const float* __restrict__ w_head, const float* __restrict__ b_head, float* __restrict__ logits,
+                      float* __restrict__ probs, float* __restrict__ features, int R, long long row_stride,
+                      long long row_off, int D, int C, float eps) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int chunks = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(r * row_stride + row_off) * D);
+  float v[kMaxChunks][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int idx = c * 32 + lane;
+    if (idx < chunks) {
+      unpack8(__ldg(xr + idx), v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[c][j];
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int idx = c * 32 + lane;
+    if (idx < chunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[c][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int idx = c * 32 + lane;
+    if (idx < chunks) {
+      const int col = idx * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + col));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + col + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + col));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(b + col + 4));
+      v[c][0] = fmaf((v[c][0] - mean) * rstd, g0.x, b0.x);
+      v[c][1] = fmaf((v[c][1] - mean) * rstd, g0.y, b0.y);
+      v[c][2] = fmaf((v[c][2] - mean) * rstd, g0.z, b0.z);
+      v[c][3] = fmaf((v[c][3] - mean) * rstd, g0.w, b0.w);
+      v[c][4] = fmaf((v[c][4] - mean) * rstd, g1.x, b1.x);
+      v[c][5] = fmaf((v[c][5] - mean) * rstd, g1.y, b1.y);
+      v[c][6] = fmaf((v[c][6] - mean) * rstd, g1.z, b1.z);
+      v[c][7] = fmaf((v[c][7] - mean) * rstd, g1.w, b1.w);
+      if (features != nullptr) {
+        float4* fr = reinterpret_cast<float4*>(features + static_cast<size_t>(r) * D + col);
+        fr[0] = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+        fr[1] = make_float4(v[c][4], v[c][5], v[c][6], v[c][7]);
+      }
+    }
+  }
+  if (w_head == nullptr) return;
+  float* lr = logits + static_cast<size_t>(r) * C;
+  float mx = -INFINITY;
+  for (int cls = 0; cls < C; ++cls) {
+    const float* wr = w_head + static_cast<size_t>(cls) * D;
+    float d = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int idx = c * 32 + lane;
+      if (idx < chunks) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr + idx * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr + idx * 8 + 4));
+        d = fmaf(v[c][0], w0.x, d); d = fmaf(v[c][1], w0.y, d); d = fmaf(v[c][2], w0.z, d); d = fmaf(v[c][3], w0.w, d);
+        d = fmaf(v[c][4], w1.x, d); d = fmaf(v[c][5], w1.y, d); d = fmaf(v[c][6], w1.z, d); d = fmaf(v[c][7], w1.w, d);
+      }
+    }
+    d = warp_sum(d) + __ldg(&b_head[cls]);
+    mx = fmaxf(mx, d);
+    if (lane == 0) lr[cls] = d;
+  }
+  if (probs == nullptr) return;
+  __syncwarp();  // lane 0's logits are visible to the warp
+  float den = 0.f;
+  for (int cls = lane; cls < C; cls += 32) den += expf(lr[cls] - mx);
+  den = warp_sum(den);
+  for (int cls = lane; cls < C; cls += 32) probs[static_cast<size_t>(r) * C + cls] = expf(lr[cls] - mx) / den;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Class token of the MVD sibling (other_models/MVD/modeling_finetune.py:431-435): x[b] = cat(cls_token, emb[b]) — the
+// token carries no position row — plus the LayerNorm statistics of every row of x for norm1 of the first block.
+// One warp per output row.  Bytes: 2 B N D read + 2 B (N + 1) D written (+ 8 B (N + 1)).
+__global__ void __launch_bounds__(256)
+prepend_cls_kernel(const bf16* __restrict__ emb, const float* __restrict__ cls_token, bf16* __restrict__ x,
+                   float2* __restrict__ stats, int B, int N, int D, float eps) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = N + 1;
+  if (row >= B * S) return;
+  const int b = row / S;
+  const int i = row - b * S;
+  const int chunks = D >> 3;
+  uint4* xr = reinterpret_cast<uint4*>(x + static_cast<size_t>(row) * D);
+  const uint4* er = reinterpret_cast<const uint4*>(emb + (static_cast<size_t>(b) * N + (i > 0 ? i - 1 : 0)) * D);
+  float v[kMaxChunks][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int idx = c * 32 + lane;
+    if (idx < chunks) {
+      uint4 u;
+      if (i > 0) {
+        u = __ldg(er + idx);
+      } else {
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(cls_token + idx * 8));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(cls_token + idx * 8 + 4));
+        u.x = pack_bf16(c0.x, c0.y);
+        u.y = pack_bf16(c0.z, c0.w);
+        u.z = pack_bf16(c1.x, c1.y);
+        u.w = pack_bf16(c1.z, c1.w);
+      }
+      xr[idx] = u;
+      unpack8(u, v[c]);  // statistics of the values as stored (bf16)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[c][j];
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int idx = c * 32 + lane;
+    if (idx < chunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[c][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float var = warp_sum(q) / static_cast<float>(D);
+  if (lane == 0) stats[row] = make_float2(mean, rsqrtf(var + eps));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -531,7 +680,8 @@ int launch_layernorm(const bf16* x, const float* g, const float* b, float* y, in
 
 int launch_pool_norm_head(const bf16* x, const float* g, const float* b, const float* w_head, const float* b_head,
                           float* logits, float* probs, float* features, float* scratch, int B, int N, int D, int C,
-                          float eps, cudaStream_t stream) {
+                          float eps, cudaStream_t stream, size_t clip_stride) {
+  if (clip_stride == 0) clip_stride = static_cast<size_t>(N) * D;
   STAD_CHECK_ARG(B > 0 && N > 0 && C > 0 && C <= 1024, "pool_norm_head: bad sizes B=%d N=%d C=%d", B, N, C);
   STAD_CHECK_ARG(D % 8 == 0 && D >= 8 && D <= 2048, "pool_norm_head: D=%d must be a multiple of 8 and <= 2048", D);
   if (reinterpret_cast<uintptr_t>(x) & 15) return fail(STAD_E_ALIGN, "pool_norm_head: x must be 16-byte aligned");
@@ -540,11 +690,45 @@ int launch_pool_norm_head(const bf16* x, const float* g, const float* b, const f
   STAD_CHECK_ARG(groups >= 1, "pool_norm_head: D too large for the pooling block");
   const size_t smem1 = static_cast<size_t>(groups) * D * sizeof(float);
   ProfScope prof(STAD_K_POOL, 0, B * N, D, 0, stream);
-  pool_partial_kernel<<<dim3(kPoolChunks, B), threads, smem1, stream>>>(x, scratch, N, D);
+  pool_partial_kernel<<<dim3(kPoolChunks, B), threads, smem1, stream>>>(x, scratch, N, D, clip_stride);
   STAD_LAUNCH_OK("pool_partial");
   const size_t smem2 = (static_cast<size_t>(D) + 32 + C) * sizeof(float);
   pool_head_kernel<<<B, threads, smem2, stream>>>(scratch, g, b, w_head, b_head, logits, probs, features, N, D, C, eps);
   STAD_LAUNCH_OK("pool_head");
+  return STAD_OK;
+}
+
+int launch_rows_norm_head(const bf16* x, const float* g, const float* b, const float* w_head, const float* b_head,
+                          float* logits, float* probs, float* features, int R, long long row_stride, long long row_off,
+                          int D, int C, float eps, cudaStream_t stream) {
+  int rc = check_row_args(x, R, D);
+  if (rc) return rc;
+  STAD_CHECK_ARG(row_stride >= 1 && row_off >= 0, "rows_norm_head: row_stride=%lld row_off=%lld", row_stride, row_off);
+  STAD_CHECK_ARG(w_head == nullptr || (b_head && logits && C > 0), "rows_norm_head: a head needs b_head, logits, C > 0");
+  STAD_CHECK_ARG(w_head != nullptr || features != nullptr, "rows_norm_head: nothing to write");
+  if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(features) |
+       reinterpret_cast<uintptr_t>(w_head)) & 15)
+    return fail(STAD_E_ALIGN, "rows_norm_head: g, b, w_head, features must be 16-byte aligned");
+  const int rows_per_block = 8;
+  ProfScope prof(STAD_K_LAYERNORM, 1, R, D, C, stream);
+  rows_norm_head_kernel<<<ceil_div(R, rows_per_block), rows_per_block * 32, 0, stream>>>(
+      x, g, b, w_head, b_head, logits, probs, features, R, row_stride, row_off, D, C, eps);
+  STAD_LAUNCH_OK("rows_norm_head");
+  return STAD_OK;
+}
+
+int launch_prepend_cls(const bf16* emb, const float* cls_token, bf16* x, float2* stats, int B, int N, int D, float eps,
+                       cudaStream_t stream) {
+  STAD_CHECK_ARG(B > 0 && N > 0, "prepend_cls: B=%d N=%d", B, N);
+  int rc = check_row_args(x, B * (N + 1), D);
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(emb) | reinterpret_cast<uintptr_t>(cls_token)) & 15)
+    return fail(STAD_E_ALIGN, "prepend_cls: emb, cls_token must be 16-byte aligned");
+  const int rows_per_block = 8;
+  ProfScope prof(STAD_K_ASSEMBLE, 1, B * (N + 1), D, 0, stream);
+  prepend_cls_kernel<<<ceil_div(B * (N + 1), rows_per_block), rows_per_block * 32, 0, stream>>>(emb, cls_token, x, stats, B,
+                                                                                             N, D, eps);
+  STAD_LAUNCH_OK("prepend_cls");
   return STAD_OK;
 }
 

@@ -297,7 +297,7 @@ def get_sinusoid_encoding_table(n_position, d_hid):
 class _PreparedModel:
     """Device-side packed weights + the ctypes stad_model that points at them (built once per weight version)."""
 
-    def __init__(self, owner, device, final_norm, head):
+    def __init__(self, owner, device, final_norm, head, reduction=_lib.STAD_REDUCE_MEAN, cls_token=None):
         pe = owner.patch_embed
         D = owner.embed_dim
         keep = []
@@ -335,12 +335,18 @@ class _PreparedModel:
         m.b_head = b_head.data_ptr() if b_head is not None else None
         m.eps = float(final_norm.eps)
         m.attn_scale = float(owner.blocks[0].attn.scale)
+        m.reduction = int(reduction)
+        if cls_token is not None:
+            cls_token = cls_token.detach().to(device=device, dtype=torch.float32).reshape(D).contiguous()
+            m.cls_token = cls_token.data_ptr()
+        self.reduction = int(reduction)
+        self.cls_rows = 0 if cls_token is None else 1
         self.model = m
         self.device = device
         self.num_classes = num_classes
         self.embed_dim = D
         self.n_tokens = pe.num_patches
-        self._keep = (keep, blocks, w_patch, pos_bias, norm_g, norm_b, w_head, b_head)
+        self._keep = (keep, blocks, w_patch, pos_bias, norm_g, norm_b, w_head, b_head, cls_token)
         self._workspace = None
         self._ws_key = None
         self._in_bf16 = None
@@ -369,9 +375,11 @@ class _PreparedModel:
         """One stad_vit_forward call. `want`: any of logits / probs / features (classifier) or tokens (encoder).
         Returns a dict of fp32 tensors."""
         lib = _lib.load()
-        ws, need = self.workspace(B, n_tok)
-        shapes = {"logits": (B, self.num_classes), "probs": (B, self.num_classes), "features": (B, self.embed_dim),
-                  "tokens": (B, n_tok, self.embed_dim)}
+        rows = n_tok + self.cls_rows                       # rows per clip in the residual stream
+        ws, need = self.workspace(B, rows)
+        per_tok = (rows,) if self.reduction == _lib.STAD_REDUCE_NONE else ()  # 'none': one result per token (mf:330)
+        shapes = {"logits": (B,) + per_tok + (self.num_classes,), "probs": (B,) + per_tok + (self.num_classes,),
+                  "features": (B,) + per_tok + (self.embed_dim,), "tokens": (B, rows, self.embed_dim)}
         res = {k: torch.empty(shapes[k], dtype=torch.float32, device=self.device) for k in want}
         outs = _lib.StadOutputs(*[res[k].data_ptr() if k in res else None for k in ("logits", "probs", "features", "tokens")])
         rc = lib.stad_vit_forward(C.byref(self.model), C.byref(inp), _lib.ptr(tok_idx), B, n_tok, C.byref(outs),
@@ -388,12 +396,12 @@ def _weights_signature(module):
 class _StadBackbone(nn.Module):
     """Shared plumbing of the classifier and the pre-training encoder: lazy weight preparation + cache."""
 
-    def _prepared_for(self, device, final_norm, head):
-        sig = (_weights_signature(self), str(device))
+    def _prepared_for(self, device, final_norm, head, reduction=_lib.STAD_REDUCE_MEAN, cls_token=None):
+        sig = (_weights_signature(self), str(device), int(reduction))
         prep = getattr(self, "_stad_prepared", None)
         if prep is None or self._stad_sig != sig:
             _lib.init(device)
-            prep = _PreparedModel(self, device, final_norm, head)
+            prep = _PreparedModel(self, device, final_norm, head, reduction, cls_token)
             object.__setattr__(self, "_stad_prepared", prep)
             object.__setattr__(self, "_stad_sig", sig)
         return prep
@@ -442,11 +450,7 @@ class VisionTransformer(_StadBackbone):
         num_patches = self.patch_embed.num_patches
         self.use_checkpoint = use_checkpoint  # activation checkpointing is a training feature: ignored at inference
 
-        if use_learnable_pos_emb:
-            self.pos_embed = nn.Parameter(torch.zeros(1, num_patches, embed_dim))
-        else:
-            # plain tensor attribute, absent from the state_dict, exactly as in the reference (mf:253)
-            self.pos_embed = get_sinusoid_encoding_table(num_patches, embed_dim)
+        self.pos_embed = self._build_pos_embed(num_patches, embed_dim, use_learnable_pos_emb)
 
         self.pos_drop = nn.Dropout(p=drop_rate)
 
@@ -466,6 +470,7 @@ class VisionTransformer(_StadBackbone):
 
         if use_learnable_pos_emb:
             trunc_normal_(self.pos_embed, std=.02)
+        self._init_extra_tokens()
 
         if hasattr(self.head, "weight"):
             trunc_normal_(self.head.weight, std=.02)
@@ -474,6 +479,16 @@ class VisionTransformer(_StadBackbone):
         if hasattr(self.head, "weight"):
             self.head.weight.data.mul_(init_scale)
             self.head.bias.data.mul_(init_scale)
+
+    def _build_pos_embed(self, num_patches, embed_dim, learnable):
+        """The position table of the model (mf:249-253).  The sibling architectures (other_models/) override this."""
+        if learnable:
+            return nn.Parameter(torch.zeros(1, num_patches, embed_dim))
+        # plain tensor attribute, absent from the state_dict, exactly as in the reference (mf:253)
+        return get_sinusoid_encoding_table(num_patches, embed_dim)
+
+    def _init_extra_tokens(self):
+        """Hook for parameters a sibling adds between the blocks and the head (MVD's class token)."""
 
     def _init_weights(self, m):
         if isinstance(m, nn.Linear):
@@ -501,17 +516,27 @@ class VisionTransformer(_StadBackbone):
     # ------------------------------------------------------------------------------------------ sm_100a forward
     def _check_supported(self):
         _inference_only(self)
-        if self.final_reduction != "fc_norm":
-            raise NotImplementedError(f"final_reduction={self.final_reduction!r}: every simple-tad script uses 'fc_norm' "
-                                      "(rff:153, ri:52, te:55); the other reductions are not on the accelerated path")
         if not isinstance(self.head, nn.Linear):
             raise NotImplementedError("num_classes=0 on VisionTransformer: use PretrainVisionTransformerEncoder for features")
         self.blocks[0].attn._check_head_dim()
 
+    def _reduction(self):
+        """final_reduction -> (STAD_REDUCE_*, the LayerNorm the kernels apply).  mf:323-330: 'fc_norm' pools and then
+        applies fc_norm (norm is Identity); 'cls' / anything else apply norm and keep token 0 / every token."""
+        if self.final_reduction == "fc_norm":
+            return _lib.STAD_REDUCE_MEAN, self.fc_norm
+        if self.final_reduction == "cls":
+            return _lib.STAD_REDUCE_CLS, self.norm
+        return _lib.STAD_REDUCE_NONE, self.norm
+
+    def _cls_token(self):
+        return None  # the simple-tad ViT has no class token; the MVD sibling overrides this
+
     def prepare(self, device=None):
         self._check_supported()
         device = device or next(self.parameters()).device
-        return self._prepared_for(torch.device(device), self.fc_norm, self.head)
+        reduction, norm = self._reduction()
+        return self._prepared_for(torch.device(device), norm, self.head, reduction, self._cls_token())
 
     def _run(self, x, want):
         self._check_supported()
@@ -552,12 +577,12 @@ class VisionTransformer(_StadBackbone):
 
     @torch.no_grad()
     def forward_features(self, x):
-        """fc_norm(mean over tokens) [B, D] (mf:308-326)."""
+        """fc_norm(mean over tokens) [B, D] (mf:308-326); 'cls': norm(x)[:, 0]; 'none': norm(x) [B, N, D] (mf:327-330)."""
         return self._run(x, want=("logits", "features"))["features"]
 
     @torch.no_grad()
     def forward(self, x):
-        """logits [B, num_classes] (mf:332-335)."""
+        """logits [B, num_classes] (mf:332-335); [B, N, num_classes] with final_reduction='none'."""
         return self._run(x, want=("logits",))["logits"]
 
     @torch.no_grad()

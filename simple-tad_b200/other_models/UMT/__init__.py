@@ -1,0 +1,1 @@
+from .modeling_finetune import *  # noqa: F401,F403

@@ -88,6 +88,23 @@ def make_state_dict(arch, seed=0, num_classes=2, encoder=False, peaky=1.0):
     return sd
 
 
+def make_variant_state_dict(arch, seed=0, num_classes=2, tubelet=TUBELET, final_reduction="fc_norm", cls_token=False):
+    """make_state_dict re-keyed for the other forms of the classifier: final_reduction 'cls' / 'none' own `norm.*`
+    instead of `fc_norm.*` (modeling_finetune.py:269-270); tubelet 1 (the UMT job) keeps the first temporal slice of
+    the Conv3d weight; cls_token adds MVD's `cls_token` [1, 1, D] (other_models/MVD/modeling_finetune.py:364-366)."""
+    D, _, _ = ARCHS[arch]
+    sd = make_state_dict(arch, seed=seed, num_classes=num_classes)
+    if tubelet != TUBELET:
+        assert tubelet == 1
+        sd["patch_embed.proj.weight"] = sd["patch_embed.proj.weight"][:, :, :1].contiguous() * math.sqrt(2.0)
+    if final_reduction != "fc_norm":
+        sd["norm.weight"] = sd.pop("fc_norm.weight")
+        sd["norm.bias"] = sd.pop("fc_norm.bias")
+    if cls_token:
+        sd["cls_token"] = 0.5 * torch.randn((1, 1, D), generator=_gen(7000 + seed))
+    return sd
+
+
 def _block_weights(sd, p, D, g):
     sd[p + "norm1.weight"] = 1.0 + 0.1 * torch.randn((D,), generator=g)
     sd[p + "norm1.bias"] = 0.05 * torch.randn((D,), generator=g)
@@ -129,9 +146,9 @@ def bf16_round(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
-def make_clips(B, seed=0):
+def make_clips(B, seed=0, frames=FRAMES, img=IMG):
     """x ~ N(0,1) [B,3,16,224,224] as in test_efficiency.py:17, rounded to bf16-representable fp32."""
-    return bf16_round(torch.randn((B, CHANS, FRAMES, IMG, IMG), generator=_gen(2000 + seed)))
+    return bf16_round(torch.randn((B, CHANS, frames, img, img), generator=_gen(2000 + seed)))
 
 
 def make_video(T, seed=0):

@@ -92,6 +92,39 @@ def check_pool_head(B=5, N=1568, D=768, Cn=2, eps=1e-6):
     return {"name": "pool_head", "logits": a, "probs": p, "features": f}
 
 
+def check_rows_norm_head(B=3, S=1568, D=768, Cn=2, rows="all", eps=1e-6, seed=60):
+    """final_reduction 'cls' / 'none' (mf:323-334): LayerNorm of token 0 / every token, head, softmax."""
+    x = (_f32(B, S, D, seed=seed, scale=1.2, shift=0.2)).to(torch.bfloat16)
+    g = _f32(D, seed=seed + 1, scale=0.2, shift=1.0)
+    b = _f32(D, seed=seed + 2, scale=0.2)
+    w = _f32(Cn, D, seed=seed + 3, scale=0.05)
+    bh = _f32(Cn, seed=seed + 4, scale=0.1)
+    logits, probs, feats = L.rows_norm_head(x, g, b, w, bh, eps, rows=rows, want_probs=True, want_features=True)
+    torch.cuda.synchronize()
+    xf = x.float()[:, 0] if rows == "cls" else x.float()
+    normed = torch.nn.functional.layer_norm(xf, (D,), g, b, eps)
+    ref = normed @ w.t() + bh
+    tag = f"rows_norm_head[{rows},B{B},S{S},D{D},C{Cn}]"
+    a = _stats(logits, ref, tag + ".logits", 2e-4, 2e-4)
+    p = _stats(probs, ref.softmax(-1), tag + ".probs", 1e-4, 1e-4)
+    f = _stats(feats, normed, tag + ".features", 1e-4, 1e-4)
+    return {"name": "rows_norm_head", "logits": a, "probs": p, "features": f}
+
+
+def check_prepend_cls(B=3, N=1568, D=384, eps=1e-6, seed=70):
+    """x = cat(cls_token, emb) per clip (MVD mf:431-435) + LayerNorm statistics of every row."""
+    emb = _bf16(B, N, D, seed=seed, scale=1.1)
+    cls = _f32(D, seed=seed + 1, scale=0.5)
+    x, st = L.prepend_cls(emb, cls, eps)
+    torch.cuda.synchronize()
+    ref = torch.cat([cls.to(torch.bfloat16)[None, None].expand(B, 1, D), emb], dim=1)
+    assert torch.equal(x, ref), f"prepend_cls[{B}x{N}x{D}]: rows are not bit-identical to torch.cat"
+    xf = ref.float().reshape(B * (N + 1), D)
+    a = _stats(st[:, 0], xf.mean(1), f"prepend_cls.mean[{B}x{N}x{D}]", 1e-5, 1e-5)
+    b = _stats(st[:, 1], (xf.var(1, unbiased=False) + eps).rsqrt(), f"prepend_cls.rstd[{B}x{N}x{D}]", 1e-5, 1e-4)
+    return {"name": "prepend_cls", "mean": a, "rstd": b}
+
+
 # ----------------------------------------------------------------------------------------------------------- GEMMs
 def check_gemm(M=1568, N=768, K=768, mode="plain", seed=0):
     """mode: plain | bias | resid | ln | ln_gelu"""
@@ -175,26 +208,26 @@ def _sinusoid(n, d):
     return tab.float()
 
 
-def check_patch_embed(B=2, D=384, mode="clips", masked=False, seed=0):
-    Cc, T, Hh, Ww = 3, 16, 224, 224
-    K = Cc * 2 * 16 * 16
-    N = 8 * 14 * 14
-    w5 = _bf16(D, Cc, 2, 16, 16, seed=seed + 31, scale=0.03)
+def check_patch_embed(B=2, D=384, mode="clips", masked=False, seed=0, T=16, tubelet=2, img=224):
+    Cc, Hh, Ww = 3, img, img
+    K = Cc * tubelet * 16 * 16
+    N = (T // tubelet) * (img // 16) ** 2
+    w5 = _bf16(D, Cc, tubelet, 16, 16, seed=seed + 31, scale=0.03)
     bias = _f32(D, seed=seed + 32, scale=0.2)
     pos_bias = (_sinusoid(N, D).to(DEV) + bias).contiguous()
-    dims = L.make_dims(dim=D, depth=1, heads=D // 64, hidden=4 * D)
+    dims = L.make_dims(img_h=img, img_w=img, tubelet=tubelet, frames=T, dim=D, depth=1, heads=D // 64, hidden=4 * D)
     if mode == "clips":
         x = _bf16(B, Cc, T, Hh, Ww, seed=seed + 33)
         clips = x
         kw = dict(mode=L.STAD_IN_CLIPS)
     else:
-        F, start, stride = 16 + 3 * (B - 1) + 2, 1, 3
+        F, start, stride = T + 3 * (B - 1) + 2, 1, 3
         frames = _bf16(F, Cc, Hh, Ww, seed=seed + 34)
         x = frames
         clips = torch.stack([frames[start + b * stride: start + b * stride + T] for b in range(B)])  # [B,T,C,H,W]
         clips = clips.permute(0, 2, 1, 3, 4).contiguous()
         kw = dict(mode=L.STAD_IN_FRAMES, n_frames=F, start=start, stride=stride)
-    ref = torch.nn.functional.conv3d(clips.float(), w5.float(), None, stride=(2, 16, 16))  # [B,D,8,14,14]
+    ref = torch.nn.functional.conv3d(clips.float(), w5.float(), None, stride=(tubelet, 16, 16))  # [B,D,8,14,14]
     ref = ref.flatten(2).transpose(1, 2) + pos_bias  # [B,N,D]
     tok_idx = None
     n_tok = N
@@ -207,7 +240,8 @@ def check_patch_embed(B=2, D=384, mode="clips", masked=False, seed=0):
         ref = torch.gather(ref, 1, tok.to(DEV)[:, :, None].expand(-1, -1, D))
     out = L.patch_embed(x, w5.reshape(D, K).contiguous(), pos_bias, dims, B, n_tok, tok_idx=tok_idx, **kw)
     torch.cuda.synchronize()
-    return _stats(out.reshape(B, n_tok, D), ref, f"patch_embed[{mode},masked={masked},B{B},D{D}]", 2e-2, 1e-2)
+    return _stats(out.reshape(B, n_tok, D), ref,
+                  f"patch_embed[{mode},masked={masked},B{B},D{D},T{T},tubelet{tubelet},img{img}]", 2e-2, 1e-2)
 
 
 # -------------------------------------------------------------------------------- MAE decoder glue / frame preparation
@@ -300,6 +334,13 @@ def check_gemm_pair():
 
 
 CHECKS = {
+    "rows_norm_head": lambda: [check_rows_norm_head(3, 1568, 768, 2, "all"), check_rows_norm_head(5, 1569, 384, 2, "cls"),
+                               check_rows_norm_head(2, 100, 1024, 40, "all", seed=61),
+                               check_rows_norm_head(4, 7, 384, 400, "cls", seed=62)],
+    "prepend_cls": lambda: [check_prepend_cls(), check_prepend_cls(2, 196, 1024, seed=71)],
+    # sequence lengths of the sibling models: 1569 = 1568 + class token (33-row / 33-key tails), 3136, 4608
+    "attention_siblings": lambda: [check_attention(2, 6, 1569, seed=7), check_attention(1, 6, 3136, seed=8),
+                                   check_attention(1, 3, 4608, peaky=3.0, seed=9)],
     "gemm_pair": check_gemm_pair,
     "resize_cubic": check_resize_cubic,
     "decoder_assemble": lambda: [check_decoder_assemble(), check_decoder_assemble(2, 1568, 392, 192, seed=50),
@@ -336,6 +377,11 @@ CHECKS = {
                                      check_attention(16, 6, 392, peaky=5.0, seed=5)],
     "patch_embed": lambda: [check_patch_embed(2, 384, "clips"), check_patch_embed(3, 768, "clips")],
     "patch_embed_frames": lambda: check_patch_embed(3, 384, "frames"),
+    # the UMT sibling's geometries: tubelet 1 (K = 768) on 8 and 16 frames, a 384 px image (24 x 24 grid, 4 h' per tile)
+    "patch_embed_siblings": lambda: [check_patch_embed(2, 768, "clips", T=8, tubelet=1, seed=3),
+                                     check_patch_embed(1, 384, "clips", T=16, tubelet=1, seed=4),
+                                     check_patch_embed(1, 384, "clips", T=8, tubelet=1, img=384, seed=5),
+                                     check_patch_embed(2, 384, "frames", T=8, tubelet=1, seed=6)],
     "patch_embed_masked": lambda: [check_patch_embed(2, 768, "clips", masked=True),
                                    check_patch_embed(2, 384, "frames", masked=True)],
 }

@@ -82,3 +82,30 @@ def build_pretrain(arch, sd, decoder_depth, device="cuda"):
         decoder_depth=decoder_depth, mlp_ratio=4, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
     model.load_state_dict(sd, strict=True)
     return model.to(device).eval()
+
+
+def build_variant(name, device="cuda"):
+    """The drop-in model of a VARIANTS fixture (final_reduction 'cls' / 'none', the MVD / UMT siblings) with the
+    reference-format state dict loaded.  Returns (model, clips, oracle pieces)."""
+    from functools import partial
+    from oracle.make_golden import variant_setup
+    family, arch, extra, sd, x, pos, red = variant_setup(name)
+    if family == "mvd":
+        from simple_tad_b200.other_models.MVD import modeling_finetune as mod
+    elif family == "umt":
+        from simple_tad_b200.other_models.UMT import modeling_finetune as mod
+    else:
+        from simple_tad_b200 import modeling_finetune as mod
+    D, depth, heads = synth.ARCHS[arch]
+    kw = dict(patch_size=16, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
+              norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=2, all_frames=16, tubelet_size=2,
+              init_scale=1.0, final_reduction="fc_norm")
+    kw.update(extra)
+    model = mod.VisionTransformer(**kw)
+    sd_load = dict(sd)
+    if isinstance(model.pos_embed, torch.nn.Parameter):  # UMT: an interpolated table is a parameter (umt:237-239)
+        sd_load["pos_embed"] = model.pos_embed.detach().clone()
+    model.load_state_dict(sd_load, strict=True)
+    if device is not None:
+        model = model.to(device)
+    return model.eval(), x, dict(family=family, arch=arch, sd=sd, pos=pos, red=red, heads=heads)

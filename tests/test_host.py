@@ -180,7 +180,7 @@ def test_inference_only_and_cuda_only():
         m.train()(torch.zeros(1, 3, 16, 224, 224))
     with pytest.raises(RuntimeError, match="CUDA"):
         m.eval()(torch.zeros(1, 3, 16, 224, 224))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):  # 'cls' / 'none' are supported; still no CPU path
         mf.VisionTransformer(embed_dim=384, depth=1, num_heads=6, num_classes=2, final_reduction="cls").eval().prepare("cpu")
     with pytest.raises(NotImplementedError, match="head_dim"):
         mf.vit_huge_patch16_224(num_classes=2).eval().prepare("cpu")
