@@ -94,7 +94,6 @@ def test_variants_vs_reference_gpu(name):
     ref_s = torch.from_numpy(g["feat_samples"])
     rel = float((feat_s - ref_s).norm() / ref_s.norm())
     assert rel <= parity.TOL_HIDDEN_REL_L2, f"{name}: feature samples rel-L2 {rel:.3e}"
-    assert parity.row_cosine_min(feat_s, ref_s) >= parity.TOL_COS
     if info["red"] == "none" and info["family"] != "mvd":
         logits2, probs = model.forward_probs(xd)
         assert probs.shape == logits.shape
