@@ -22,20 +22,24 @@ import torch
 import torch.distributed as dist
 
 from . import modeling_finetune  # noqa: F401  (registers the vit_* factories, as `import modeling_finetune` does at te:9)
+from .other_models.MVD import modeling_finetune as _mvd  # noqa: F401  (registers mvd_vit_*, te:10)
 from .registry import create_model
 
 MODEL_NAMES = {"VideoMAE-S": "vit_small_patch16_224", "VideoMAE-B": "vit_base_patch16_224",
-               "VideoMAE-L": "vit_large_patch16_224", "ViViT-B": "vit_base_patch16_224"}  # te:22-118 (+ ViT-L)
+               "VideoMAE-L": "vit_large_patch16_224", "ViViT-B": "vit_base_patch16_224",   # te:22-57, te:96-113 (+ ViT-L)
+               "MVD-S": "mvd_vit_small_patch16_224", "MVD-B": "mvd_vit_base_patch16_224"}  # te:58-95
 
 
 def build(model_type, with_flash=False, device="cuda"):
-    """The create_model call of te:24-55, kwarg for kwarg (drop_block_rate=None is filtered by create_model)."""
+    """The create_model call of te:24-95, kwarg for kwarg (drop_block_rate=None is filtered by create_model)."""
     if model_type not in MODEL_NAMES:
-        raise ValueError(f"{model_type!r}: this path covers {sorted(MODEL_NAMES)} (MVD / InternVideo2 are other model "
-                         "families, SURVEY §8f rank 4)")
+        raise ValueError(f"{model_type!r}: this path covers {sorted(MODEL_NAMES)} (InternVideo2 is another model "
+                         "family: different blocks, patch 14)")
+    extra = {"use_cls_token": False} if model_type.startswith("MVD") else {}   # te:72, te:91
     model = create_model(MODEL_NAMES[model_type], pretrained=False, num_classes=2, all_frames=16, tubelet_size=2,
                          fc_drop_rate=0.0, drop_rate=0.0, drop_path_rate=0.1, attn_drop_rate=0.0, drop_block_rate=None,
-                         use_checkpoint=False, final_reduction="fc_norm", init_scale=0.001, use_flash_attn=with_flash)
+                         use_checkpoint=False, final_reduction="fc_norm", init_scale=0.001, use_flash_attn=with_flash,
+                         **extra)
     return model.to(device).eval()
 
 

@@ -226,6 +226,8 @@ def test_efficiency_harness_and_cuda_graph_replay():
     assert res["params"] == 21_880_706 and res["avg_ms"] > 0 and res["fps"] > 0
     rows = efficiency.batch_sweep("VideoMAE-S", batches=(1, 3), warmup=2, iters=3, quiet=True)
     assert [r["batch_per_gpu"] for r in rows] == [1, 3] and all(r["clips_per_s"] > 0 for r in rows)
+    res = efficiency.main("MVD-S", with_flash=True, steps=5, quiet=True)   # te:58-76: same size, 3-D sin-cos table
+    assert res["params"] == 21_880_706 and res["avg_ms"] > 0
 
 
 def test_eval_epilogue_counts_are_exact_and_metrics_match_the_reference():
