@@ -31,9 +31,49 @@ def timed(fn, iters, warmup=3):
     return e0.elapsed_time(e1) / iters
 
 
+def siblings(iters, dev, peak):
+    """The sibling classifiers at ViT-B width: MVD with / without its class token, UMT on 8 and 16 frames
+    with tubelet 1, and the per-token 'none' reduction.  FLOPs per clip from SURVEY §8d's formula with the model's own
+    token count S and patch-embed K."""
+    from functools import partial
+    from simple_tad_b200.other_models.MVD import modeling_finetune as mvd
+    from simple_tad_b200.other_models.UMT import modeling_finetune as umt
+    D, L = 768, 12
+    common = dict(patch_size=16, embed_dim=D, depth=L, num_heads=12, mlp_ratio=4, qkv_bias=True,
+                  norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=2, init_scale=1.0)
+    cases = [
+        ("MVD-B (3-D sin-cos table), fc_norm", mvd.VisionTransformer, dict(), 64, 16, 2, "fc_norm", False),
+        ("MVD-B + class token (S = 1569), fc_norm", mvd.VisionTransformer, dict(use_cls_token=True), 64, 16, 2, "fc_norm", True),
+        ("UMT-B tubelet 1 x 8 frames (S = 1568), fc_norm", umt.VisionTransformer, dict(), 64, 8, 1, "fc_norm", False),
+        ("UMT-B tubelet 1 x 16 frames (S = 3136), fc_norm", umt.VisionTransformer, dict(), 24, 16, 1, "fc_norm", False),
+        ("ViT-B final_reduction='none' (per-token logits)", mf.VisionTransformer, dict(), 64, 16, 2, "none", False),
+        ("ViT-B final_reduction='cls'", mf.VisionTransformer, dict(), 64, 16, 2, "cls", False),
+    ]
+    for name, cls, extra, B, frames, tubelet, red, cls_tok in cases:
+        model = cls(all_frames=frames, tubelet_size=tubelet, final_reduction=red, **common, **extra)
+        sd = synth.make_variant_state_dict("vit_base_patch16_224", seed=0, tubelet=tubelet, final_reduction=red,
+                                           cls_token=cls_tok)
+        if isinstance(model.pos_embed, torch.nn.Parameter):
+            sd["pos_embed"] = model.pos_embed.detach().clone()
+        model.load_state_dict(sd)
+        model = model.to(dev).eval()
+        clips = [synth.make_clips(B, seed=90 + i, frames=frames).to(dev).to(torch.bfloat16) for i in range(2)]
+        ms = timed(lambda i: model(clips[i % 2]), iters)
+        n_patch = (frames // tubelet) * 196
+        S = n_patch + (1 if cls_tok else 0)
+        gf = (2 * n_patch * 3 * tubelet * 256 * D + L * (24 * S * D * D + 4 * S * S * D)) / 1e9
+        cps = B / (ms * 1e-3)
+        print(json.dumps({"config": f"{name}, {B} clips/step", "ms_per_step": ms, "clips_per_s": cps, "gflop_per_clip": gf,
+                          "model_tflops": cps * gf / 1e3, "frac_of_sustained_peak": cps * gf / 1e3 / peak,
+                          "launches": model.prepare().last_launches}), flush=True)
+        del model, clips
+        torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--siblings", action="store_true", help="only the MVD / UMT / reduction variants")
     a = ap.parse_args()
     dev = torch.device("cuda")
     peak = 1374.5
@@ -41,6 +81,8 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
     except Exception:
         pass
+    if a.siblings:
+        return siblings(a.iters, dev, peak)
     for arch, B in (("vit_small_patch16_224", 128), ("vit_base_patch16_224", 64), ("vit_large_patch16_224", 32)):
         model = mf.__dict__[arch](num_classes=2, all_frames=16, tubelet_size=2, init_scale=1.0, final_reduction="fc_norm")
         model.load_state_dict(synth.make_state_dict(arch, seed=0))
