@@ -125,7 +125,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   // single-lane TMA / tcgen05.mma issue below takes its operands straight from uniform registers
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int num_tiles = (kPair ? p.m_tiles / 2 : p.m_tiles) * p.n_tiles;
+  // pair mode with an odd number of M-tiles: the last pair's second M-tile lies wholly beyond row M — its TMA loads
+  // return zeros, its stores are clipped and every per-row access is guarded by row_ok
+  const int num_tiles = (kPair ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
   const int num_kb = p.K / BK;
   auto m_tile_of = [&](int tile) { return kPair ? 2 * (tile / p.n_tiles) + static_cast<int>(cta_rank) : tile / p.n_tiles; };
 
@@ -587,7 +589,7 @@ template <int EPI>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                 const KArgs& ka, cudaStream_t stream) {
   using C = Cfg<256, true>;
-  const int tiles = (ka.m_tiles / 2) * ka.n_tiles;
+  const int tiles = ((ka.m_tiles + 1) / 2) * ka.n_tiles;
   const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
   ProfScope prof(STAD_K_GEMM, EPI | 64, ka.M, ka.N, ka.K, stream);
   STAD_CUDA_OK(launch_pdl(gemm_kernel<256, EPI, false, true>, dim3(2 * pairs), dim3(kThreads), C::SMEM_BYTES, stream, 2, ta,
@@ -610,6 +612,14 @@ int pair_min_k() {
     return e ? atoi(e) : 0;
   }();
   return k;
+}
+// STAD_GEMM_PAIR_ODD=0: shapes with an odd number of M-tiles stay on the single-CTA tile (A/B measurements).
+bool pair_odd_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("STAD_GEMM_PAIR_ODD");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 // STAD_GEMM_PAIR=0 in the environment keeps every GEMM on the single-CTA tile (A/B measurements).
 bool pair_enabled() {
@@ -751,14 +761,14 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   }
   const int bn = pick_bn(ka.m_tiles, g.N);
   ka.n_tiles = g.N / bn;
-  // CTA-pair tiles (256 x 256) when the shape allows: full-width column tiles, an even number of M-tiles, at least one
-  // tile per pair, and an epilogue that has a pair instantiation
+  // CTA-pair tiles (256 x 256) when the shape allows: full-width column tiles, at least one tile per pair, and an
+  // epilogue that has a pair instantiation (an odd M-tile count is padded with a virtual, fully clipped M-tile)
   const bool pair_epi = g.epi == 0 || g.epi == EPI_LN || g.epi == (EPI_LN | EPI_GELU) || g.epi == EPI_RESID ||
                         g.epi == (EPI_RESID | EPI_STATS);
   // (measured, B = 64 ViT-B, single-CTA -> pair tile with the warp-private epilogue: qkv 259 -> 232 us, fc1 387 -> 346,
   // fc2 337 -> 318, proj 118 -> 118)
-  const bool pair = pair_enabled() && !g.patch && bn == 256 && ka.m_tiles % 2 == 0 && pair_epi &&
-                    g.K >= pair_min_k() && (ka.m_tiles / 2) * ka.n_tiles >= sm_count() / 2;
+  const bool pair = pair_enabled() && !g.patch && bn == 256 && (ka.m_tiles % 2 == 0 || pair_odd_enabled()) && pair_epi &&
+                    g.K >= pair_min_k() && ((ka.m_tiles + 1) / 2) * ka.n_tiles >= sm_count() / 2;
   {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
     const uint64_t strides[1] = {(uint64_t)g.K * 2};

@@ -330,6 +330,13 @@ def check_gemm_pair():
         out.append(check_gemm(M, N, K, mode, seed=60 + len(out)))
     out.append(check_gemm_stats(9472, 768, 512, 3072, seed=7))      # first GEMM: resid + stats on the pair tile
     out.append(check_gemm_stats(25088 - 128 - 5, 1024, 256, 4096, seed=8))
+    # odd number of M-tiles: the last pair's second M-tile is virtual (zero-filled loads, clipped stores); 16000 rows =
+    # the DAPT encoder batch (100 clips x 160 visible tokens), 100416 = 64 clips x 1569 tokens (MVD class token)
+    for M, N, K, mode in ((9600, 512, 2048, "plain"), (9600 - 37, 512, 768, "ln"), (16000, 3072, 768, "ln_gelu"),
+                          (16000, 768, 3072, "resid"), (9600 - 128 - 1, 768, 768, "bias")):
+        out.append(check_gemm(M, N, K, mode, seed=80 + len(out)))
+    out.append(check_gemm_stats(16000, 768, 2304, 768, seed=9))
+    out.append(check_gemm_stats(9600 - 91, 1024, 512, 4096, seed=10))
     return out
 
 
