@@ -1,4 +1,5 @@
 // extern "C" surface of libstad.so (declared in include/stad.h) and the host-side sequencing of one forward.
+#include <cstdlib>
 #include <mutex>
 
 #include "kernels.h"
@@ -62,8 +63,16 @@ int make_geom(const stad_dims* d, const stad_input* in, int B, PatchGeom* pg) {
   return STAD_OK;
 }
 
-// Up to this many rows the LN-folded GEMMs finish the LayerNorm statistics themselves (see run_blocks)
+// Up to this many rows the LN-folded GEMMs finish the LayerNorm statistics themselves (see run_blocks).
+// STAD_FOLD_STATS_MAX_ROWS overrides it (A/B measurements).
 constexpr int kFoldStatsMaxRows = 8192;
+int fold_stats_max_rows() {
+  static const int v = [] {
+    const char* e = getenv("STAD_FOLD_STATS_MAX_ROWS");
+    return e ? atoi(e) : kFoldStatsMaxRows;
+  }();
+  return v;
+}
 
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
@@ -173,7 +182,7 @@ int run_blocks(const stad_block* blocks, const stad_dims* d, float eps, float at
   const int M = B * n_tok;
   const int D = d->dim;
   const int parts_resid = gemm_stat_parts(M, D, false, nullptr);
-  const bool fold_stats = M <= kFoldStatsMaxRows;
+  const bool fold_stats = M <= fold_stats_max_rows();
   int parts = parts_in;
   int rc;
   for (int l = 0; l < d->depth; ++l) {
