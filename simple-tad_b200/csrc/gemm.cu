@@ -515,12 +515,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               tma_store_wait_read<2>();   // slot of chunk ci + 2 was last stored from by chunk ci - 2
               prefetch_residual(ci + 2);
             }
-          } else if (c & 1) {
+          } else if ((c & 1) || c == CHUNKS - 1) {
             // Without a residual the stores leave two chunks at a time: fence.proxy.async stalls the issuing lane while
             // bulk stores of the CTA are still in flight, and half a tile after the previous batch they no longer are.
+            // (Three chunks per warpgroup, BN = 192: a batch of two, then the last chunk alone.)
             if (elect_one()) {
               fence_proxy_async_smem();
-              tma_store_2d(&tmap_out, buf - kWarpSlotBytes, n0 - kSubCols, tr.row0 + quarter * 32);
+              if (c & 1)
+                tma_store_2d(&tmap_out, stage_buf + ((ci - 1) & (kWarpSlots - 1)) * kWarpSlotBytes, n0 - kSubCols,
+                             tr.row0 + quarter * 32);
               tma_store_2d(&tmap_out, buf, n0, tr.row0 + quarter * 32);
               tma_store_commit();
             }
@@ -585,24 +588,46 @@ int set_smem() {
 }
 
 // CTA-pair variant (256 x 256 tiles, cta_group::2): launched as clusters of two CTAs, one pair per TPC.
-template <int EPI>
-int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                const KArgs& ka, cudaStream_t stream) {
-  using C = Cfg<256, true>;
+template <int BN, int EPI>
+int launch_pair_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                   const KArgs& ka, cudaStream_t stream) {
+  using C = Cfg<BN, true>;
   const int tiles = ((ka.m_tiles + 1) / 2) * ka.n_tiles;
   const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
   ProfScope prof(STAD_K_GEMM, EPI | 64, ka.M, ka.N, ka.K, stream);
-  STAD_CUDA_OK(launch_pdl(gemm_kernel<256, EPI, false, true>, dim3(2 * pairs), dim3(kThreads), C::SMEM_BYTES, stream, 2, ta,
+  STAD_CUDA_OK(launch_pdl(gemm_kernel<BN, EPI, false, true>, dim3(2 * pairs), dim3(kThreads), C::SMEM_BYTES, stream, 2, ta,
                           tb, to, tr, ka));
   STAD_LAUNCH_OK("gemm_kernel (CTA pair)");
   return STAD_OK;
+}
+
+// 256 x 256 tiles; 256 x 192 where 256 does not divide N (N = 384, 1152: ViT-S, the MAE decoder) only on request
+template <int EPI>
+int launch_pair(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                const KArgs& ka, cudaStream_t stream) {
+  if (bn == 192) return launch_pair_bn<192, EPI>(ta, tb, to, tr, ka, stream);
+  return launch_pair_bn<256, EPI>(ta, tb, to, tr, ka, stream);
 }
 
 template <int EPI>
 int set_smem_pair() {
   STAD_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<256, EPI, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg<256, true>::SMEM_BYTES));
+  STAD_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<192, EPI, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg<192, true>::SMEM_BYTES));
   return STAD_OK;
+}
+
+// 256 x 192 pair tiles are OFF by default: measured slower than the single-CTA 192-column tile on every shape that
+// would use them (ViT-S 6407 -> 6260 clips/s, full MAE forward 11.48 k -> 11.09 k; profiles/r1c_pair192_ab.txt) — with
+// K = 384 the mainloop is six k-blocks long and the tile is bound by its epilogue, which the pair does not shorten.
+// STAD_GEMM_PAIR_192=1 enables them (A/B measurements; results are identical, tests/kernel_checks.py::check_gemm_pair).
+bool pair_192_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("STAD_GEMM_PAIR_192");
+    return e && e[0] == '1';
+  }();
+  return on;
 }
 
 // STAD_GEMM_PAIR_MIN_K overrides the K from which the pair tile is used (development).
@@ -767,7 +792,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
                         g.epi == (EPI_RESID | EPI_STATS);
   // (measured, B = 64 ViT-B, single-CTA -> pair tile with the warp-private epilogue: qkv 259 -> 232 us, fc1 387 -> 346,
   // fc2 337 -> 318, proj 118 -> 118)
-  const bool pair = pair_enabled() && !g.patch && bn == 256 && (ka.m_tiles % 2 == 0 || pair_odd_enabled()) && pair_epi &&
+  const bool pair = pair_enabled() && !g.patch && (bn == 256 || (bn == 192 && pair_192_enabled())) &&
+                    (ka.m_tiles % 2 == 0 || pair_odd_enabled()) && pair_epi &&
                     g.K >= pair_min_k() && ((ka.m_tiles + 1) / 2) * ka.n_tiles >= sm_count() / 2;
   {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
@@ -794,11 +820,11 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   }
   if (pair) {
     switch (g.epi) {
-      case 0: return launch_pair<0>(ta, tb, to, tr, ka, stream);
-      case EPI_LN: return launch_pair<EPI_LN>(ta, tb, to, tr, ka, stream);
-      case EPI_LN | EPI_GELU: return launch_pair<EPI_LN | EPI_GELU>(ta, tb, to, tr, ka, stream);
-      case EPI_RESID: return launch_pair<EPI_RESID>(ta, tb, to, tr, ka, stream);
-      case EPI_RESID | EPI_STATS: return launch_pair<EPI_RESID | EPI_STATS>(ta, tb, to, tr, ka, stream);
+      case 0: return launch_pair<0>(bn, ta, tb, to, tr, ka, stream);
+      case EPI_LN: return launch_pair<EPI_LN>(bn, ta, tb, to, tr, ka, stream);
+      case EPI_LN | EPI_GELU: return launch_pair<EPI_LN | EPI_GELU>(bn, ta, tb, to, tr, ka, stream);
+      case EPI_RESID: return launch_pair<EPI_RESID>(bn, ta, tb, to, tr, ka, stream);
+      case EPI_RESID | EPI_STATS: return launch_pair<EPI_RESID | EPI_STATS>(bn, ta, tb, to, tr, ka, stream);
     }
   }
   switch (g.epi) {

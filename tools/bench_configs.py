@@ -75,6 +75,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--siblings", action="store_true", help="only the MVD / UMT / reduction variants")
     ap.add_argument("--dapt-only", action="store_true", help="only the masked encoder / MAE forward lines")
+    ap.add_argument("--small-only", action="store_true", help="of the classifiers, only ViT-S")
     a = ap.parse_args()
     dev = torch.device("cuda")
     peak = 1374.5
@@ -84,8 +85,8 @@ def main():
         pass
     if a.siblings:
         return siblings(a.iters, dev, peak)
-    for arch, B in (() if a.dapt_only else (("vit_small_patch16_224", 128), ("vit_base_patch16_224", 64),
-                                            ("vit_large_patch16_224", 32))):
+    classifiers = (("vit_small_patch16_224", 128), ("vit_base_patch16_224", 64), ("vit_large_patch16_224", 32))
+    for arch, B in (() if a.dapt_only else classifiers[:1] if a.small_only else classifiers):
         model = mf.__dict__[arch](num_classes=2, all_frames=16, tubelet_size=2, init_scale=1.0, final_reduction="fc_norm")
         model.load_state_dict(synth.make_state_dict(arch, seed=0))
         model = model.to(dev).eval()
