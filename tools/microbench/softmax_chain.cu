@@ -1,0 +1,89 @@
+// Microbenchmark (B200): the per-tile chain of one attention softmax warp WITHOUT the tensor core and without barriers —
+//   tcgen05.ld of a score row (NCH x 32 fp32 columns) -> row max -> exp2(s*c - m) + row sum + bf16 pack per chunk ->
+//   tcgen05.st of the packed P row -> wait
+// for W softmax warps per SM sub-partition.  It bounds what the softmax side of attention_kernel can sustain for a
+// given (warps per sub-partition, keys per tile) design: today 2 x 128; candidates 3 x 96 (three query tiles per CTA,
+// P written over S) and 4 x 64.  Output: clocks per tile per warp and score elements / clk / SM.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o softmax_chain softmax_chain.cu ; run on the GPU box.
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../simple-tad_b200/csrc/softmax_math.cuh"
+using namespace stad;
+
+template <int NCH, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k(int iters, long long* out, float* sink, float c) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) { tmem_alloc<512>(&slot); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  // warps w, w+4, w+8, ... share lane quarter w & 3; each gets its own column range (S at col0, P over the same columns)
+  const int group = warp >> 2;
+  const uint32_t col0 = static_cast<uint32_t>(group * NCH * 32) & 511u;
+  const uint32_t base = slot + (static_cast<uint32_t>((warp & 3) * 32) << 16) + col0;
+  {  // something finite to read
+    uint32_t z[32];
+    for (int i = 0; i < 32; ++i) z[i] = __float_as_uint(-0.01f * (lane + i));
+    for (int ch = 0; ch < NCH; ++ch) tmem_st32(base + ch * 32, z);
+    tmem_st_wait();
+  }
+  float a0 = 0.f, a1 = 0.f, m_run = -1e30f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t s[NCH][32];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) tmem_ld32(base + ch * 32, s[ch]);
+    tmem_ld_wait();
+    float mx = chunk_max(s[0]);
+#pragma unroll
+    for (int ch = 1; ch < NCH; ++ch) mx = fmaxf(mx, chunk_max(s[ch]));
+    m_run = fmaxf(m_run, mx * c);
+    const float neg_m = -m_run;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      uint32_t pk[16];
+      exp_chunk<true>(s[ch], c, neg_m, a0, a1, pk);
+      tmem_st16(base + ch * 16, pk);  // P (bf16 pairs) over the first half of the chunk's own S columns
+    }
+    tmem_st_wait();
+  }
+  const long long t1 = clock64();
+  if (lane == 0) out[blockIdx.x * 32 + warp] = t1 - t0;
+  if (a0 + a1 + m_run == 123.456f) sink[0] = a0;
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(slot); }
+}
+
+template <int NCH, int WPS>
+void run(long long* out, float* sink) {
+  constexpr int THREADS = WPS * 4 * 32;
+  const int iters = 3000;
+  long long h[32];
+  for (int rep = 0; rep < 2; ++rep) {
+    k<NCH, THREADS><<<148, THREADS>>>(iters, out, sink, 0.18f);
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(cudaGetLastError())); return; }
+  }
+  cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+  long long mxc = 0;
+  for (int w = 0; w < WPS * 4; ++w) mxc = h[w] > mxc ? h[w] : mxc;
+  const double per_tile = static_cast<double>(mxc) / iters;
+  const double elems = static_cast<double>(iters) * NCH * 32 * 32 * WPS * 4;
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, k<NCH, THREADS>);
+  printf("%d warps/sub-partition x %3d keys/tile: %7.1f clk per tile per warp, %6.2f elements/clk/SM, "
+         "%6.1f clk per 256 x 128 scores  (%d regs/thread)\n",
+         WPS, NCH * 32, per_tile, elems / mxc, 256.0 * 128.0 / (elems / mxc), fa.numRegs);
+}
+
+int main() {
+  long long* out; float* sink;
+  cudaMalloc(&out, 148 * 32 * 8); cudaMalloc(&sink, 4);
+  run<4, 1>(out, sink);
+  run<4, 2>(out, sink);   // today's kernel: 2 x 128
+  run<3, 2>(out, sink);
+  run<3, 3>(out, sink);   // candidate: three query tiles per CTA, 96-key tiles
+  run<2, 3>(out, sink);
+  run<2, 4>(out, sink);   // four query tiles, 64-key tiles
+  run<4, 3>(out, sink);   // 3 x 128 (TMEM would not allow it; register-pressure reference)
+  return 0;
+}
