@@ -10,7 +10,25 @@
 #include "../../simple-tad_b200/csrc/softmax_math.cuh"
 using namespace stad;
 
-template <int NCH, int THREADS>
+// exp2 + pack of a chunk WITHOUT the row-sum adds (what the loop costs if the row sum came out of the tensor core: a
+// ones column appended to V makes P·[V | 1] deliver it in a 65th accumulator column)
+STAD_DEVICE void exp_chunk_nosum(const uint32_t (&s)[32], float c, float neg_m, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float x0, x1, e0, e1;
+    fma2(x0, x1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), c, c, neg_m, neg_m);
+    if (kPolyPeriod > 0 && (i % (kPolyPeriod > 0 ? kPolyPeriod : 1)) == (kPolyPeriod - 1)) {
+      exp2_poly2(e0, e1, x0, x1);
+    } else {
+      e0 = ex2(x0);
+      e1 = ex2(x1);
+    }
+    pk[i] = pack_bf16(e0, e1);
+  }
+}
+
+// MODE bit 0: no row-sum adds; bit 1: no row max (a reference maximum is assumed known, e.g. from the previous tile)
+template <int NCH, int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS, 1) k(int iters, long long* out, float* sink, float c) {
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -34,15 +52,20 @@ __global__ void __launch_bounds__(THREADS, 1) k(int iters, long long* out, float
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) tmem_ld32(base + ch * 32, s[ch]);
     tmem_ld_wait();
-    float mx = chunk_max(s[0]);
+    if constexpr (!(MODE & 2)) {
+      float mx = chunk_max(s[0]);
 #pragma unroll
-    for (int ch = 1; ch < NCH; ++ch) mx = fmaxf(mx, chunk_max(s[ch]));
-    m_run = fmaxf(m_run, mx * c);
+      for (int ch = 1; ch < NCH; ++ch) mx = fmaxf(mx, chunk_max(s[ch]));
+      m_run = fmaxf(m_run, mx * c);
+    } else {
+      m_run = fmaxf(m_run, __uint_as_float(s[0][it & 31]) * c);
+    }
     const float neg_m = -m_run;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       uint32_t pk[16];
-      exp_chunk<true>(s[ch], c, neg_m, a0, a1, pk);
+      if constexpr (MODE & 1) exp_chunk_nosum(s[ch], c, neg_m, pk);
+      else exp_chunk<true>(s[ch], c, neg_m, a0, a1, pk);
       tmem_st16(base + ch * 16, pk);  // P (bf16 pairs) over the first half of the chunk's own S columns
     }
     tmem_st_wait();
@@ -54,13 +77,13 @@ __global__ void __launch_bounds__(THREADS, 1) k(int iters, long long* out, float
   if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(slot); }
 }
 
-template <int NCH, int WPS>
+template <int NCH, int WPS, int MODE = 0>
 void run(long long* out, float* sink) {
   constexpr int THREADS = WPS * 4 * 32;
   const int iters = 3000;
   long long h[32];
   for (int rep = 0; rep < 2; ++rep) {
-    k<NCH, THREADS><<<148, THREADS>>>(iters, out, sink, 0.18f);
+    k<NCH, THREADS, MODE><<<148, THREADS>>>(iters, out, sink, 0.18f);
     if (cudaDeviceSynchronize() != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(cudaGetLastError())); return; }
   }
   cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
@@ -69,10 +92,11 @@ void run(long long* out, float* sink) {
   const double per_tile = static_cast<double>(mxc) / iters;
   const double elems = static_cast<double>(iters) * NCH * 32 * 32 * WPS * 4;
   cudaFuncAttributes fa;
-  cudaFuncGetAttributes(&fa, k<NCH, THREADS>);
-  printf("%d warps/sub-partition x %3d keys/tile: %7.1f clk per tile per warp, %6.2f elements/clk/SM, "
+  cudaFuncGetAttributes(&fa, k<NCH, THREADS, MODE>);
+  printf("%d warps/sub-partition x %3d keys/tile%s%s: %7.1f clk per tile per warp, %6.2f elements/clk/SM, "
          "%6.1f clk per 256 x 128 scores  (%d regs/thread)\n",
-         WPS, NCH * 32, per_tile, elems / mxc, 256.0 * 128.0 / (elems / mxc), fa.numRegs);
+         WPS, NCH * 32, (MODE & 1) ? ", no row sum" : "", (MODE & 2) ? ", no row max" : "", per_tile, elems / mxc,
+         256.0 * 128.0 / (elems / mxc), fa.numRegs);
 }
 
 int main() {
@@ -85,5 +109,11 @@ int main() {
   run<2, 3>(out, sink);
   run<2, 4>(out, sink);   // four query tiles, 64-key tiles
   run<4, 3>(out, sink);   // 3 x 128 (TMEM would not allow it; register-pressure reference)
+  // which instruction group the chain is bound by
+  run<4, 2, 1>(out, sink);
+  run<4, 2, 2>(out, sink);
+  run<4, 2, 3>(out, sink);
+  run<3, 2, 1>(out, sink);
+  run<3, 2, 3>(out, sink);
   return 0;
 }
