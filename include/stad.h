@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define STAD_ABI_VERSION 4
+#define STAD_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define STAD_API __attribute__((visibility("default")))
@@ -51,8 +51,10 @@ enum {
 /* Where the clips of a batch live. */
 enum {
   STAD_IN_CLIPS = 0, /* x[B, C, T, H, W] bf16 — the tensor VisionTransformer.forward receives (mf:332)          */
-  STAD_IN_FRAMES = 1 /* frames[F, C, H, W] bf16 of ONE video; clip b = frames[start + b*stride, +T) — the
-                        sliding window of ri:69-109 / ris:428-465 / dota.py:204-223 without materialising it */
+  STAD_IN_FRAMES = 1 /* frames[F, C, H, W] bf16 of ONE video; frame t of clip b = frames[start + b*stride + t*frame_step]
+                        — the sliding window of ri:69-109 / ris:428-465 / dota.py:204-223 without materialising it;
+                        frame_step = orig_fps / target_fps is the in-window subsampling of RegularSequencer
+                        (dataset/sequencing.py:45-58: DADA-2000 is read at 30 fps and scored at 10 fps, dada.py:31)   */
 };
 
 typedef struct stad_input {
@@ -61,6 +63,7 @@ typedef struct stad_input {
   int32_t n_frames; /* FRAMES: F (number of frames resident); CLIPS: ignored */
   int32_t start;    /* FRAMES: first frame of clip 0 */
   int32_t stride;   /* FRAMES: frame step between consecutive clips (1 = every window, dota.py:209) */
+  int32_t frame_step; /* FRAMES: frame distance inside a clip; 0 or 1 = consecutive frames */
 } stad_input;
 
 /* Geometry of one model (PatchEmbed mf:172-183, VisionTransformer mf:211-234). */

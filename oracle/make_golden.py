@@ -350,6 +350,28 @@ def gen_variant(name):
          hid_ch=np.array(HID_CH))
 
 
+SEQ_CASES = [  # (timesteps_nb, input_frequency, seq_frequency, seq_length, step)
+    (100, 10, 10, 16, 1), (16, 10, 10, 16, 1), (15, 10, 10, 16, 1), (100, 10, 10, 16, 10), (103, 10, 10, 16, 7),
+    (150, 30, 10, 16, 1), (150, 30, 10, 16, 3), (151, 30, 10, 16, 10), (46, 30, 10, 16, 1), (45, 30, 10, 16, 1),
+    (90, 30, 10, 8, 10), (64, 20, 10, 8, 5), (200, 30, 30, 16, 4),
+]
+
+
+def gen_sequences(name):
+    """RegularSequencer.get_sequences of the unmodified dataset/sequencing.py (dota.py:209-213, dada.py:173-177) on a
+    grid of video lengths / frame rates / steps: pins simple_tad_b200.sequencing.window_plan."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_stad_ref_sequencing", os.path.join(REF, "dataset", "sequencing.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = {"cases": np.array(SEQ_CASES)}
+    for i, (T, fin, fseq, length, step) in enumerate(SEQ_CASES):
+        seqs = mod.RegularSequencer(seq_frequency=fseq, seq_length=length, step=step).get_sequences(T, fin)
+        out[f"seq_{i}"] = np.zeros((0, length), dtype=np.int64) if seqs is None else np.array(seqs, dtype=np.int64)
+        print(f"  {SEQ_CASES[i]}: {0 if seqs is None else len(seqs)} windows")
+    save(name, **out)
+
+
 def main():
     install_shims()
     torch.set_num_threads(os.cpu_count())
@@ -380,6 +402,8 @@ def main():
         gen_pretrain("c4_mae_vitb_b2", "vit_base_patch16_224", B=2, seed=6, decoder_depth=4)
     if on("c5"):
         gen_classifier("c5_vitb_b8", "vit_base_patch16_224", B=8, seed=5)
+    if on("sequencer"):
+        gen_sequences("sequencer")
     for name in VARIANTS:
         if on("variants") or (want and name in want):
             gen_variant(name)

@@ -26,7 +26,7 @@ EXPORTS = (
 
 class StadInput(C.Structure):
     _fields_ = [("data", C.c_void_p), ("mode", C.c_int32), ("n_frames", C.c_int32), ("start", C.c_int32),
-                ("stride", C.c_int32)]
+                ("stride", C.c_int32), ("frame_step", C.c_int32)]
 
 
 class StadDims(C.Structure):
@@ -325,11 +325,12 @@ def make_dims(img_h=224, img_w=224, patch=16, tubelet=2, frames=16, in_chans=3, 
     return StadDims(img_h, img_w, patch, tubelet, frames, in_chans, dim, depth, heads, hidden, num_classes)
 
 
-def make_input(data, mode=STAD_IN_CLIPS, n_frames=0, start=0, stride=1):
-    return StadInput(data.data_ptr(), mode, n_frames, start, stride)
+def make_input(data, mode=STAD_IN_CLIPS, n_frames=0, start=0, stride=1, frame_step=1):
+    return StadInput(data.data_ptr(), mode, n_frames, start, stride, frame_step)
 
 
-def patch_embed(x, w, pos_bias, dims, B, n_tok, tok_idx=None, mode=STAD_IN_CLIPS, n_frames=0, start=0, stride=1):
+def patch_embed(x, w, pos_bias, dims, B, n_tok, tok_idx=None, mode=STAD_IN_CLIPS, n_frames=0, start=0, stride=1,
+                frame_step=1):
     """x: bf16 planes ([B,C,T,H,W] clips or [F,C,H,W] frames) -> [B*n_tok, D] bf16."""
     init(x.device)
     _req(x, torch.bfloat16, "x")
@@ -341,7 +342,7 @@ def patch_embed(x, w, pos_bias, dims, B, n_tok, tok_idx=None, mode=STAD_IN_CLIPS
     if tok_idx is not None:
         _req(tok_idx, torch.int32, "tok_idx")
         gather = torch.empty(B * n_tok, w.shape[1], dtype=torch.bfloat16, device=x.device)
-    inp = make_input(x, mode, n_frames, start, stride)
+    inp = make_input(x, mode, n_frames, start, stride, frame_step)
     check(load().stad_patch_embed(C.byref(inp), ptr(w), ptr(pos_bias), ptr(tok_idx), ptr(out), ptr(gather),
                                   C.byref(dims), B, n_tok, stream_ptr()), "stad_patch_embed")
     return out

@@ -47,15 +47,17 @@ int make_geom(const stad_dims* d, const stad_input* in, int B, PatchGeom* pg) {
   pg->mode = in->mode;
   pg->start = in->start;
   pg->stride = in->stride;
+  pg->fstep = in->frame_step > 1 ? in->frame_step : 1;
   if (in->mode == STAD_IN_CLIPS) {
     pg->n_planes = B * d->in_chans * d->frames;
     pg->start = 0;
     pg->stride = 0;
   } else if (in->mode == STAD_IN_FRAMES) {
     STAD_CHECK_ARG(in->stride >= 1 && in->start >= 0, "frames input: start=%d stride=%d", in->start, in->stride);
-    STAD_CHECK_ARG(in->start + (B - 1) * in->stride + d->frames <= in->n_frames,
+    STAD_CHECK_ARG(in->frame_step >= 0, "frames input: frame_step=%d", in->frame_step);
+    STAD_CHECK_ARG(in->start + (B - 1) * in->stride + (d->frames - 1) * pg->fstep < in->n_frames,
                    "frames input: clip %d needs frame %d but only %d frames are resident", B - 1,
-                   in->start + (B - 1) * in->stride + d->frames - 1, in->n_frames);
+                   in->start + (B - 1) * in->stride + (d->frames - 1) * pg->fstep, in->n_frames);
     pg->n_planes = in->n_frames * d->in_chans;
   } else {
     return fail(STAD_E_SHAPE, "unknown input mode %d", in->mode);

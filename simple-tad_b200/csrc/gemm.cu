@@ -205,7 +205,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int dh0 = (kb & 3) * 4;
             const int t = pe_tp * g.tubelet + dt;
             const int plane = g.mode == STAD_IN_CLIPS ? (pe_b * g.C + c) * g.T + t
-                                                      : (g.start + pe_b * g.stride + t) * g.C + c;
+                                                      : (g.start + pe_b * g.stride + t * g.fstep) * g.C + c;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)  // K-slice k = line dh0 + k: [tokens][16 dw] at sa + k * 4 KB
               tma_load_5d(sa + k * (BM * UMMA_K * 2), &tmap_a, &full_bar[stage], 0, 0, pe_h0, dh0 + k, plane);

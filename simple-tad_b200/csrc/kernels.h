@@ -12,6 +12,7 @@ struct PatchGeom {
   int C, T, tubelet;
   int img_h, img_w;
   int mode, start, stride;  // STAD_IN_CLIPS / STAD_IN_FRAMES
+  int fstep;                // FRAMES: frame distance inside a clip (>= 1)
   int n_planes;             // extent of the plane dimension of the input tensor map
 };
 

@@ -406,7 +406,7 @@ gather_patches_kernel(const bf16* __restrict__ planes, PatchGeom pg, const int32
   const int dt = (k >> 8) % pg.tubelet;
   const int c = (k >> 8) / pg.tubelet;
   const int t = tp * pg.tubelet + dt;
-  const int plane = pg.mode == STAD_IN_CLIPS ? (b * pg.C + c) * pg.T + t : (pg.start + b * pg.stride + t) * pg.C + c;
+  const int plane = pg.mode == STAD_IN_CLIPS ? (b * pg.C + c) * pg.T + t : (pg.start + b * pg.stride + t * pg.fstep) * pg.C + c;
   const size_t src = (static_cast<size_t>(plane) * pg.img_h + hp * 16 + dh) * pg.img_w + wp * 16 + dw;
   reinterpret_cast<uint4*>(out)[i] = __ldg(reinterpret_cast<const uint4*>(planes + src));
 }

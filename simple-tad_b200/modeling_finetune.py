@@ -556,22 +556,26 @@ class VisionTransformer(_StadBackbone):
         return prep.run(inp, B, pe.num_patches, want=want)
 
     @torch.no_grad()
-    def forward_windows(self, frames, start=0, count=None, stride=1):
+    def forward_windows(self, frames, start=0, count=None, stride=1, frame_step=1):
         """Sliding-window inference straight from a resident frame buffer (ri:69-109, dota.py:204-223):
-        frames [F, C, H, W] (fp32 or bf16, already normalised); window b covers frames [start + b*stride, +T).
+        frames [F, C, H, W] (fp32 or bf16, already normalised); frame t of window b is frames[start + b*stride +
+        t*frame_step] (frame_step = orig_fps // target_fps, dataset/sequencing.py:45-58; 1 = consecutive frames).
         Returns (logits, probs), each [count, num_classes], without materialising the [count, C, T, H, W] clips."""
         self._check_supported()
         if frames.dim() != 4 or not frames.is_cuda:
             raise ValueError(f"expected CUDA frames [F, C, H, W], got {tuple(frames.shape)} on {frames.device}")
         F_ = frames.shape[0]
         T = self.num_frames
+        if frame_step < 1 or stride < 1:
+            raise ValueError(f"stride={stride} and frame_step={frame_step} must be >= 1")
+        span = (T - 1) * frame_step + 1                      # frames a window covers (sequencing.py:48-50)
         if count is None:
-            count = (F_ - T - start) // stride + 1
+            count = (F_ - span - start) // stride + 1
         if count < 1:
-            raise ValueError(f"{F_} frames hold no window of {T} frames from start={start}")
+            raise ValueError(f"{F_} frames hold no window of {T} frames (frame step {frame_step}) from start={start}")
         prep = self.prepare(frames.device)
         fb = prep.input_bf16(frames)
-        inp = _lib.make_input(fb, _lib.STAD_IN_FRAMES, n_frames=F_, start=start, stride=stride)
+        inp = _lib.make_input(fb, _lib.STAD_IN_FRAMES, n_frames=F_, start=start, stride=stride, frame_step=frame_step)
         res = prep.run(inp, count, self.patch_embed.num_patches, want=("logits", "probs"))
         return res["logits"], res["probs"]
 

@@ -137,10 +137,6 @@ class VisionTransformer(_VisionTransformer):
             return _lib.STAD_REDUCE_MEAN, self.fc_norm
         return _lib.STAD_REDUCE_CLS, self.norm
 
-    def forward_windows(self, frames, start=0, count=None, stride=1):
-        if self.use_cls_token:
-            raise NotImplementedError("forward_windows with a class token: materialise the clips and call forward()")
-        return super().forward_windows(frames, start=start, count=count, stride=stride)
 
 
 def _factory(name, embed_dim, depth, num_heads):

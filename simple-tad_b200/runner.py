@@ -43,13 +43,15 @@ def gather_scores(local, n_total, group=None):
     return out[:n_total]
 
 
-def window_segments(video_lengths, lo, hi, frames_per_clip=16, stride=1):
+def window_segments(video_lengths, lo, hi, frames_per_clip=16, stride=1, frame_step=1):
     """Map the global window range [lo, hi) onto (video, first_window, n_windows) segments.
-    A video of T frames has (T - frames_per_clip) // stride + 1 windows (sequencing.py:38-62)."""
+    A video of T frames has (T - span) // stride + 1 windows, span = (frames_per_clip - 1) * frame_step + 1
+    (sequencing.py:38-62, simple_tad_b200.sequencing.window_plan)."""
     segs = []
     base = 0
+    span = (frames_per_clip - 1) * frame_step + 1
     for v, T in enumerate(video_lengths):
-        n = (T - frames_per_clip) // stride + 1 if T >= frames_per_clip else 0
+        n = (T - span) // stride + 1 if T >= span else 0
         a, b = max(lo, base), min(hi, base + n)
         if a < b:
             segs.append((v, a - base, b - a))
@@ -60,12 +62,17 @@ def window_segments(video_lengths, lo, hi, frames_per_clip=16, stride=1):
 class SlidingWindowRunner:
     """Scores every 16-frame window of one or many videos with a VisionTransformer of this package."""
 
-    def __init__(self, model, batch_windows=64, device=None, stride=1):
+    def __init__(self, model, batch_windows=64, device=None, stride=1, frame_step=1):
+        """stride: source frames between consecutive windows (`view_step`, dota.py:209); frame_step: source frames
+        between consecutive frames of a window (orig_fps // target_fps: 3 for DADA-2000, dada.py:31).  Windows are
+        aligned to the end of a video, as RegularSequencer aligns them (sequencing.py:53-60)."""
         self.model = model.eval()
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         self.batch_windows = int(batch_windows)
         self.stride = int(stride)
+        self.frame_step = int(frame_step)
         self.T = model.num_frames
+        self.span = (self.T - 1) * self.frame_step + 1
         self._dev_frames = None
         self._norm_frames = None
 
@@ -82,16 +89,18 @@ class SlidingWindowRunner:
 
     @torch.no_grad()
     def score_frames_device(self, frames):
-        """frames [F, C, H, W] (host or device) -> (logits, probs) [F - T + 1 (strided), num_classes] on the device."""
+        """frames [F, C, H, W] (host or device) -> (logits, probs) [(F - span) // stride + 1, num_classes] on the device."""
         dev = self._upload(frames)
         F_ = dev.shape[0]
-        n = (F_ - self.T) // self.stride + 1
-        if n < 1:
-            raise ValueError(f"need at least {self.T} frames, got {F_}")
+        n = (F_ - self.span) // self.stride + 1
+        if F_ < self.span:
+            raise ValueError(f"need at least {self.span} frames, got {F_}")
+        first = (F_ - self.span) % self.stride      # the last window ends on the last frame (sequencing.py:55)
         logits, probs = [], []
         for w0 in range(0, n, self.batch_windows):
             cnt = min(self.batch_windows, n - w0)
-            lg, pr = self.model.forward_windows(dev, start=w0 * self.stride, count=cnt, stride=self.stride)
+            lg, pr = self.model.forward_windows(dev, start=first + w0 * self.stride, count=cnt, stride=self.stride,
+                                                frame_step=self.frame_step)
             logits.append(lg)
             probs.append(pr)
         return (logits[0], probs[0]) if len(logits) == 1 else (torch.cat(logits), torch.cat(probs))
@@ -138,13 +147,14 @@ class SlidingWindowRunner:
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank(group) if world > 1 else 0
         lengths = [int(v.shape[0]) for v in videos]
-        _, n_total = window_segments(lengths, 0, 0, self.T, self.stride)
+        _, n_total = window_segments(lengths, 0, 0, self.T, self.stride, self.frame_step)
         lo, hi, per = shard_range(n_total, world, rank)
-        segs, _ = window_segments(lengths, lo, hi, self.T, self.stride)
+        segs, _ = window_segments(lengths, lo, hi, self.T, self.stride, self.frame_step)
         outs = []
         for v, w0, cnt in segs:
-            f0 = w0 * self.stride
-            f1 = (w0 + cnt - 1) * self.stride + self.T
+            first = (lengths[v] - self.span) % self.stride
+            f0 = first + w0 * self.stride
+            f1 = first + (w0 + cnt - 1) * self.stride + self.span
             lg, _ = self.score_frames_device(videos[v][f0:f1])
             outs.append(lg.clone())
         C = self.model.num_classes
@@ -162,16 +172,17 @@ class SlidingWindowRunner:
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank(group) if world > 1 else 0
         lengths = [int(v.shape[0]) for v in videos]
-        _, n_total = window_segments(lengths, 0, 0, self.T, self.stride)
+        _, n_total = window_segments(lengths, 0, 0, self.T, self.stride, self.frame_step)
         lo, hi, per = shard_range(n_total, world, rank)
-        segs, _ = window_segments(lengths, lo, hi, self.T, self.stride)
+        segs, _ = window_segments(lengths, lo, hi, self.T, self.stride, self.frame_step)
         outs, labs = [], []
         for v, w0, cnt in segs:
-            f0 = w0 * self.stride
-            f1 = (w0 + cnt - 1) * self.stride + self.T
+            first = (lengths[v] - self.span) % self.stride
+            f0 = first + w0 * self.stride
+            f1 = first + (w0 + cnt - 1) * self.stride + self.span
             lg, _ = self.score_frames_device(videos[v][f0:f1])
             outs.append(lg.clone())
-            last = torch.arange(w0, w0 + cnt) * self.stride + self.T - 1
+            last = first + torch.arange(w0, w0 + cnt) * self.stride + self.span - 1
             labs.append(torch.as_tensor(frame_labels[v])[last].to(torch.int32))
         C = self.model.num_classes
         if outs:

@@ -208,7 +208,7 @@ def _sinusoid(n, d):
     return tab.float()
 
 
-def check_patch_embed(B=2, D=384, mode="clips", masked=False, seed=0, T=16, tubelet=2, img=224):
+def check_patch_embed(B=2, D=384, mode="clips", masked=False, seed=0, T=16, tubelet=2, img=224, frame_step=1):
     Cc, Hh, Ww = 3, img, img
     K = Cc * tubelet * 16 * 16
     N = (T // tubelet) * (img // 16) ** 2
@@ -221,12 +221,13 @@ def check_patch_embed(B=2, D=384, mode="clips", masked=False, seed=0, T=16, tube
         clips = x
         kw = dict(mode=L.STAD_IN_CLIPS)
     else:
-        F, start, stride = T + 3 * (B - 1) + 2, 1, 3
+        span = (T - 1) * frame_step + 1  # frame t of clip b = frames[start + b*stride + t*frame_step]
+        F, start, stride = span + 3 * (B - 1) + 2, 1, 3
         frames = _bf16(F, Cc, Hh, Ww, seed=seed + 34)
         x = frames
-        clips = torch.stack([frames[start + b * stride: start + b * stride + T] for b in range(B)])  # [B,T,C,H,W]
-        clips = clips.permute(0, 2, 1, 3, 4).contiguous()
-        kw = dict(mode=L.STAD_IN_FRAMES, n_frames=F, start=start, stride=stride)
+        clips = torch.stack([frames[start + b * stride: start + b * stride + span: frame_step] for b in range(B)])
+        clips = clips.permute(0, 2, 1, 3, 4).contiguous()  # [B,T,C,H,W] -> [B,C,T,H,W]
+        kw = dict(mode=L.STAD_IN_FRAMES, n_frames=F, start=start, stride=stride, frame_step=frame_step)
     ref = torch.nn.functional.conv3d(clips.float(), w5.float(), None, stride=(tubelet, 16, 16))  # [B,D,8,14,14]
     ref = ref.flatten(2).transpose(1, 2) + pos_bias  # [B,N,D]
     tok_idx = None
@@ -391,7 +392,10 @@ CHECKS = {
     "attention_persistent": lambda: [check_attention(5, 12, 1568, seed=3), check_attention(40, 12, 160, seed=4),
                                      check_attention(16, 6, 392, peaky=5.0, seed=5)],
     "patch_embed": lambda: [check_patch_embed(2, 384, "clips"), check_patch_embed(3, 768, "clips")],
-    "patch_embed_frames": lambda: check_patch_embed(3, 384, "frames"),
+    "patch_embed_frames": lambda: [check_patch_embed(3, 384, "frames"),
+                                   # in-window frame step 3: a 30 fps video scored at 10 fps (sequencing.py:45-58)
+                                   check_patch_embed(3, 384, "frames", frame_step=3, seed=7),
+                                   check_patch_embed(2, 768, "frames", masked=True, frame_step=2, seed=8)],
     # the UMT sibling's geometries: tubelet 1 (K = 768) on 8 and 16 frames, a 384 px image (24 x 24 grid, 4 h' per tile)
     "patch_embed_siblings": lambda: [check_patch_embed(2, 768, "clips", T=8, tubelet=1, seed=3),
                                      check_patch_embed(1, 384, "clips", T=16, tubelet=1, seed=4),

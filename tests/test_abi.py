@@ -41,8 +41,9 @@ def test_abi_version_and_error_string(lib):
 
 
 def test_struct_layouts_match_header(lib):
-    # stad_input: pointer + 4 x int32; stad_dims: 11 x int32; stad_block: 10 pointers; stad_outputs: 4 pointers
-    assert ctypes.sizeof(lib.StadInput) == 24
+    # stad_input: pointer + 5 x int32 (+ 4 bytes of tail padding); stad_dims: 11 x int32; stad_block: 10 pointers;
+    # stad_outputs: 4 pointers
+    assert ctypes.sizeof(lib.StadInput) == 32
     assert ctypes.sizeof(lib.StadDims) == 44
     assert ctypes.sizeof(lib.StadBlock) == 80
     assert ctypes.sizeof(lib.StadOutputs) == 32

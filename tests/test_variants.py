@@ -101,11 +101,39 @@ def test_variants_vs_reference_gpu(name):
 
 
 @pytest.mark.gpu
-def test_mvd_windows_equal_clips_gpu():
-    """MVD without a class token through the sliding-window frame path (the MVD-B DoTA job evaluates frame-level)."""
-    model, x, info = parity.build_variant("var_mvd_vits_d2_b2", device="cuda")
+@pytest.mark.parametrize("name", ["var_mvd_vits_d2_b2", "var_mvd_clstok_vits_d2_b2"])
+def test_mvd_windows_equal_clips_gpu(name):
+    """MVD (with and without its class token) through the sliding-window frame path (the MVD-B DoTA job evaluates
+    frame-level): windows read out of the frame buffer == materialised clips, bit for bit."""
+    model, x, info = parity.build_variant(name, device="cuda")
     frames = parity.synth.make_video(20, seed=3).to("cuda")
     lw, pw = model.forward_windows(frames)
     clips = parity.synth.windows_from_video(frames.cpu()).to("cuda")
     lc = model(clips)
     assert torch.equal(lw, lc)
+
+
+@pytest.mark.gpu
+def test_frame_step_windows_follow_the_sequencer_gpu():
+    """A 30 fps video scored at 10 fps (DADA-2000, dada.py:31,173-177): the windows the kernel reads with
+    frame_step = 3 are the index lists of RegularSequencer (tests/golden/sequencer.npz), and the runner scores exactly
+    those, aligned to the last frame."""
+    from simple_tad_b200 import sequencing
+    from simple_tad_b200.runner import SlidingWindowRunner
+    model, _, _ = parity.build_variant("var_mvd_vits_d2_b2", device="cuda")
+    T_video, step = 58, 5
+    frames = parity.synth.make_video(T_video, seed=5)
+    plan = sequencing.window_plan(T_video, input_frequency=30, seq_frequency=10, seq_length=16, step=step)
+    assert plan.frame_step == 3 and plan.count == 3 and plan.start == 2
+    idx = torch.tensor(plan.sequences())                                        # [count, 16] source frame indices
+    clips = frames[idx].permute(0, 2, 1, 3, 4).contiguous().to("cuda")          # [count, C, T, H, W]
+    ref = model(clips)
+    got, _ = model.forward_windows(frames.to("cuda"), start=plan.start, count=plan.count, stride=plan.stride,
+                                   frame_step=plan.frame_step)
+    assert torch.equal(got, ref)
+    runner = SlidingWindowRunner(model, batch_windows=2, stride=step, frame_step=3)
+    lg, _ = runner.score_frames(frames)
+    assert torch.equal(lg, ref.cpu())
+    lg_all = runner.score_videos([frames, frames[:50]])
+    plan2 = sequencing.window_plan(50, 30, 10, 16, step)
+    assert lg_all.shape[0] == plan.count + plan2.count and torch.equal(lg_all[: plan.count].cpu(), ref.cpu())
