@@ -131,9 +131,12 @@ def test_frame_step_windows_follow_the_sequencer_gpu():
     got, _ = model.forward_windows(frames.to("cuda"), start=plan.start, count=plan.count, stride=plan.stride,
                                    frame_step=plan.frame_step)
     assert torch.equal(got, ref)
-    runner = SlidingWindowRunner(model, batch_windows=2, stride=step, frame_step=3)
+    runner = SlidingWindowRunner(model, batch_windows=8, stride=step, frame_step=3)   # one batch: same tiles as `ref`
     lg, _ = runner.score_frames(frames)
     assert torch.equal(lg, ref.cpu())
     lg_all = runner.score_videos([frames, frames[:50]])
     plan2 = sequencing.window_plan(50, 30, 10, 16, step)
     assert lg_all.shape[0] == plan.count + plan2.count and torch.equal(lg_all[: plan.count].cpu(), ref.cpu())
+    # batches of two windows: other tile shapes, so equal within the parity tolerance rather than bit for bit
+    lg2, _ = SlidingWindowRunner(model, batch_windows=2, stride=step, frame_step=3).score_frames(frames)
+    parity.check_logits(lg2, ref, "frame-step windows, batches of 2")
