@@ -107,3 +107,60 @@ def test_metric_count_tables_all_reduce_world_size_2_gloo(tmp_path):
         got = M.counts_from_hist(h.numpy())
         assert np.array_equal(got["tp"], counts[:, 3]) and np.array_equal(got["tn"], counts[:, 0])
         assert M.argmax_metrics(c.numpy())["confmat"] == mo.argmax_metrics(probs, labels)["confmat"]
+
+
+class _IndexModel(torch.nn.Module):
+    """Stand-in for the classifier on the host side of the runner: 'scores' a window with (video marker, index of its
+    last source frame), read out of the frame tensor itself, so any window mis-addressing shows in the gathered table."""
+
+    def __init__(self, frames_per_clip=16):
+        super().__init__()
+        self.p = torch.nn.Parameter(torch.zeros(1))
+        self.num_frames, self.num_classes = frames_per_clip, 2
+
+    def forward_windows(self, frames, start=0, count=None, stride=1, frame_step=1):
+        last = start + torch.arange(count) * stride + (self.num_frames - 1) * frame_step
+        first = start + torch.arange(count) * stride
+        # frame i of video v holds 1000 * v + i in every element
+        assert torch.equal(frames[first, 0, 0, 0] + (self.num_frames - 1) * frame_step, frames[last, 0, 0, 0])
+        lg = torch.stack([frames[last, 0, 0, 0], frames[first, 0, 0, 0]], 1).float()
+        return lg, lg.softmax(-1)
+
+
+def _videos(lengths):
+    return [(1000.0 * v + torch.arange(T, dtype=torch.float32)).view(T, 1, 1, 1).expand(T, 3, 2, 2).contiguous()
+            for v, T in enumerate(lengths)]
+
+
+def _runner_worker(rank, world, port, tmp, lengths, stride, frame_step):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from simple_tad_b200.runner import SlidingWindowRunner
+    runner = SlidingWindowRunner(_IndexModel(), batch_windows=4, device="cpu", stride=stride, frame_step=frame_step)
+    full = runner.score_videos(_videos(lengths))
+    torch.save(full, os.path.join(tmp, f"s{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("stride,frame_step,in_fps", [(1, 1, 10), (5, 3, 30), (10, 1, 10)])
+def test_score_videos_windows_follow_the_sequencer_world_size_2_gloo(tmp_path, stride, frame_step, in_fps):
+    """The sharded runner scores exactly the windows RegularSequencer lists (dataset/sequencing.py:38-62): end-aligned,
+    `stride` source frames apart, `frame_step` source frames between the frames of a window; video by video, in order,
+    identical on both ranks."""
+    from simple_tad_b200.sequencing import window_plan
+    lengths = [58, 50, 46, 40, 100, 16]
+    world = 2
+    mp.spawn(_runner_worker, args=(world, _free_port(), str(tmp_path), lengths, stride, frame_step), nprocs=world, join=True)
+    rows = []
+    for v, T in enumerate(lengths):
+        plan = window_plan(T, in_fps, 10, 16, stride)
+        if plan is None:
+            continue
+        assert plan.frame_step == frame_step
+        rows += [(1000.0 * v + seq[-1], 1000.0 * v + seq[0]) for seq in plan.sequences()]
+    want = torch.tensor(rows, dtype=torch.float32)
+    for r in range(world):
+        got = torch.load(os.path.join(str(tmp_path), f"s{r}.pt"))
+        assert got.shape == want.shape and torch.equal(got, want), f"rank {r}: window table differs from the sequencer's"
