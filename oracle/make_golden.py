@@ -233,6 +233,13 @@ def gen_eval_metrics(name):
             assert np.allclose(mine[k], ref_list, atol=1e-12), f"oracle thresholded {k} differs from the reference"
         b = mo.torchmetrics_binned(probs[:, 1], labels)
         print(f"{name}[seed {seed}, n {n}]: sklearn auroc {auroc:.6f} ap {ap:.6f}; binned(101) auroc {b['auroc']:.6f} ap {b['ap']:.6f}")
+        # the group summaries of anaysis/metrics.py:19-125 (exact AP / AUROC over every score; false-negative shares of
+        # the positives)
+        pos = probs[labels == 1, 1]
+        ones = np.ones(len(pos), dtype=np.int64)
+        out.update({f"calc_metrics_s{seed}": np.array(ref_metrics.calculate_metrics(probs[:, 1], labels)),
+                    f"fn_group_s{seed}": np.array([ref_metrics.calculate_fn_group(pos, ones)]),
+                    f"fn_group_thr_s{seed}": np.array(ref_metrics.calculate_fn_group_thresholds(pos, ones))})
         out.update({f"probs_s{seed}": probs, f"labels_s{seed}": labels, f"mcc_s{seed}": np.array(mcc_t),
                     f"precision_s{seed}": np.array(p_t), f"recall_s{seed}": np.array(r_t), f"acc_s{seed}": np.array(acc_t),
                     f"f1_s{seed}": np.array(f1_t), f"at05_s{seed}": np.array([acc, prec, rec, f1]),
@@ -387,6 +394,8 @@ def main():
         gen_masks("tube_masks")
         gen_eval_metrics("eval_metrics")
         gen_resize("resize_cubic")
+    if want and "eval_metrics" in want:
+        gen_eval_metrics("eval_metrics")
     if on("peaky"):
         gen_classifier("peaky_vits_d2_b2", "vit_small_d2", B=2, seed=13, peaky=3.0)
     # the five BASELINE.json configs

@@ -1,5 +1,6 @@
 """Evaluation epilogue of frame-level inference — the metrics `final_test` computes after the score gather
-(engine_for_frame_finetuning.py:448-497) and the per-threshold tables of anaysis/metrics.py:133-207.
+(engine_for_frame_finetuning.py:448-497), the per-threshold tables of anaysis/metrics.py:133-207 and the exact
+(un-binned) group summaries of anaysis/metrics.py:19-125.
 
 The reduction over the n per-frame scores runs on the device (`stad_eval_hist`: one pass, exact integer counts against
 the 101 THRESHOLDS); what is left is arithmetic on a [2, 102] integer table, done here in float64.  The counts are
@@ -115,6 +116,81 @@ def evaluate(probs, labels, thresholds=THRESHOLDS, group=None):
     res.update(binned_curves(c, thresholds))
     res["thresholded"] = thresholded_metrics(c)
     return res
+
+
+# ---- exact (un-binned) summaries of anaysis/metrics.py:19-125, on the host ----------------------------------------------
+# The analysis scripts of the reference re-read predictions.csv and call scikit-learn on every score (no threshold grid),
+# which needs the scores in sorted order; that is a host-side, once-per-evaluation step here as well (numpy, float64).
+
+def _distinct_score_counts(p_risk, labels):
+    """Cumulative (true positives, false positives) at the last element of every run of equal scores, scores descending
+    (what sklearn's _binary_clf_curve returns), and the class totals."""
+    p = np.asarray(p_risk, dtype=np.float64)
+    y = np.asarray(labels).astype(np.int64)
+    order = np.argsort(-p, kind="mergesort")
+    ps, ys = p[order], y[order]
+    last = np.r_[np.nonzero(np.diff(ps))[0], y.size - 1]
+    tps = np.cumsum(ys)[last].astype(np.float64)
+    return tps, (1 + last) - tps, int(y.sum()), int(y.size - y.sum())
+
+
+def exact_ap(p_risk, labels):
+    """average_precision_score (anaysis/metrics.py:54): one PR point per DISTINCT score (ties enter together),
+    AP = sum_k (R_k - R_{k-1}) P_k; 0 when there is no positive (sklearn sets recall to one and warns)."""
+    tps, fps, n_pos, _ = _distinct_score_counts(p_risk, labels)
+    if n_pos == 0:
+        return 0.0
+    return float(np.sum(np.diff(np.r_[0.0, tps / n_pos]) * (tps / (tps + fps))))
+
+
+def exact_auroc(p_risk, labels):
+    """roc_auc_score (anaysis/metrics.py:56): trapezoid area under the ROC curve with one point per distinct score.
+    ValueError when only one class is present."""
+    tps, fps, n_pos, n_neg = _distinct_score_counts(p_risk, labels)
+    if n_pos == 0 or n_neg == 0:
+        raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
+    tpr, fpr = np.r_[0.0, tps / n_pos], np.r_[0.0, fps / n_neg]
+    return float(np.sum(np.diff(fpr) * (tpr[1:] + tpr[:-1]) / 2.0))
+
+
+def exact_auroc_ap(p_risk, labels):
+    return exact_auroc(p_risk, labels), exact_ap(p_risk, labels)
+
+
+def calculate_metrics(probs, labels):
+    """anaysis/metrics.py:19-64: (acc, precision, recall, f1) of `probs >= 0.5`, exact mAP, exact AUROC.  A group that
+    holds one class only gets auc = -10 - label, the reference's fallback (anaysis/metrics.py:57-63); note that the
+    scikit-learn installed in this image (1.9) no longer raises there but warns and returns nan, so the unmodified
+    reference run here yields nan for such a group — the written fallback is what is implemented."""
+    p = np.asarray(probs, dtype=np.float64)
+    y = np.asarray(labels).astype(np.int64)
+    pred = (p >= 0.5).astype(np.int64)
+    tp = float(np.sum((pred == 1) & (y == 1)))
+    fp = float(np.sum((pred == 1) & (y == 0)))
+    fn = float(np.sum((pred == 0) & (y == 1)))
+    tn = float(np.sum((pred == 0) & (y == 0)))
+    d = lambda a, b: a / b if b else 0.0  # noqa: E731
+    acc, precision, recall, f1 = d(tp + tn, tp + tn + fp + fn), d(tp, tp + fp), d(tp, tp + fn), d(2 * tp, 2 * tp + fp + fn)
+    ap = exact_ap(p, y)
+    try:
+        auc = exact_auroc(p, y)
+    except ValueError:
+        classes = sorted(set(y.tolist()))
+        assert len(classes) == 1
+        auc = -10 - classes[0]   # -10: only "normal" frames in the group, -11: only "abnormal"
+    return acc, precision, recall, f1, ap, auc
+
+
+def calculate_fn_group(probs, labels):
+    """anaysis/metrics.py:67-92: share of a (all-positive) group scored below 0.5."""
+    return float(np.sum(np.asarray(probs, dtype=np.float64) < 0.5) / len(labels))
+
+
+def calculate_fn_group_thresholds(probs, labels, thresholds=THRESHOLDS):
+    """anaysis/metrics.py:95-125: that share at every threshold.  Equals fn / (fn + tp) of `evaluate(...)["counts"]` for
+    an all-positive group."""
+    p = np.asarray(probs)
+    return [float(np.sum(~(p >= t)) / len(labels)) for t in thresholds]
 
 
 def stats_lines(res):

@@ -184,3 +184,31 @@ def test_inference_only_and_cuda_only():
         mf.VisionTransformer(embed_dim=384, depth=1, num_heads=6, num_classes=2, final_reduction="cls").eval().prepare("cpu")
     with pytest.raises(NotImplementedError, match="head_dim"):
         mf.vit_huge_patch16_224(num_classes=2).eval().prepare("cpu")
+
+
+def test_exact_group_metrics_match_reference_metrics_py():
+    """anaysis/metrics.py:19-125 — calculate_metrics (exact AP / AUROC over every score, metrics at 0.5) and the
+    false-negative shares of a positive group — against the outputs of the unmodified reference (scikit-learn) stored
+    in tests/golden/eval_metrics.npz; plus the written one-class fallback (auc = -10 - label)."""
+    import numpy as np
+    from simple_tad_b200 import metrics as M
+    from tests import parity
+    g = parity.golden("eval_metrics")
+    for seed in (0, 1):
+        probs, labels = g[f"probs_s{seed}"], g[f"labels_s{seed}"]
+        got = np.array(M.calculate_metrics(probs[:, 1], labels))
+        assert np.allclose(got, g[f"calc_metrics_s{seed}"], rtol=0, atol=1e-12)
+        auroc, ap = M.exact_auroc_ap(probs[:, 1], labels)
+        assert abs(auroc - g[f"sk_auroc_ap_s{seed}"][0]) <= 1e-12 and abs(ap - g[f"sk_auroc_ap_s{seed}"][1]) <= 1e-12
+        pos = probs[labels == 1, 1]
+        ones = np.ones(len(pos), dtype=np.int64)
+        assert abs(M.calculate_fn_group(pos, ones) - g[f"fn_group_s{seed}"][0]) <= 1e-15
+        thr = np.array(M.calculate_fn_group_thresholds(pos, ones))
+        assert np.array_equal(thr, g[f"fn_group_thr_s{seed}"])
+        # the same shares from the count table of the device epilogue: fn / (fn + tp) of an all-positive group
+        thr32 = np.asarray(M.THRESHOLDS, dtype=np.float64).astype(np.float32)
+        hist = np.zeros((2, 102), dtype=np.int64)
+        np.add.at(hist, (ones, np.searchsorted(thr32, pos, side="right")), 1)
+        c = M.counts_from_hist(hist)
+        assert np.allclose(c["fn"] / (c["fn"] + c["tp"]), thr, rtol=0, atol=1e-15)
+        assert M.calculate_metrics(pos, ones)[5] == -11 and M.calculate_metrics(probs[labels == 0, 1], np.zeros(int((labels == 0).sum())))[5] == -10
