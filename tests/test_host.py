@@ -212,3 +212,28 @@ def test_exact_group_metrics_match_reference_metrics_py():
         c = M.counts_from_hist(hist)
         assert np.allclose(c["fn"] / (c["fn"] + c["tp"]), thr, rtol=0, atol=1e-15)
         assert M.calculate_metrics(pos, ones)[5] == -11 and M.calculate_metrics(probs[labels == 0, 1], np.zeros(int((labels == 0).sum())))[5] == -10
+
+
+def test_run_inference_simple_dropin_structure():
+    """run_inference_simple.py:279-407: VisionTransformerInfer and its two factories keep the checkpoint contract of the
+    classifier (same keys / shapes), scale the head by init_scale = 0.001, and have no CPU path; prepare_image is the
+    arithmetic of ris:18-37."""
+    import numpy as np
+    from simple_tad_b200 import run_inference_simple as ris
+    small, base = ris.get_video_vit_small(with_flash=False), ris.get_video_vit_base(with_flash=True)
+    ref_small = mf.vit_small_patch16_224(num_classes=2)
+    assert {k: tuple(v.shape) for k, v in small.state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in ref_small.state_dict().items()}
+    assert base.embed_dim == 768 and len(base.blocks) == 12 and base.num_heads == 12 and small.num_heads == 6
+    assert float(small.head.weight.abs().max()) < 1e-3 and small.final_reduction == "fc_norm"
+    with pytest.raises(RuntimeError, match="CUDA"):
+        small.eval()(torch.zeros(1, 3, 16, 224, 224))
+    g = np.random.default_rng(0)
+    img = g.integers(0, 256, size=(7, 9, 3), dtype=np.uint8)           # BGR, as cv2.imread returns it
+    got = ris.prepare_image(img, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+    want = torch.from_numpy(img[:, :, ::-1].transpose(2, 0, 1).copy()).float().div(255.0)
+    want = (want - torch.tensor((0.485, 0.456, 0.406)).view(3, 1, 1)) / torch.tensor((0.229, 0.224, 0.225)).view(3, 1, 1)
+    assert got.shape == (3, 7, 9) and got.dtype == torch.float32 and torch.equal(got, want)
+    with pytest.raises(TypeError):
+        ris.prepare_image(img[:, :, 0], (0.5,), (0.5,))
+    assert sorted(["f10.png", "f2.png", "f1.png"], key=ris._natural_key) == ["f1.png", "f2.png", "f10.png"]

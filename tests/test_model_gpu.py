@@ -60,6 +60,19 @@ def test_config1_vits_batch4():
     assert feats.shape == (4, 384) and torch.isfinite(feats).all()
 
 
+def test_run_inference_simple_model_returns_probabilities():
+    """run_inference_simple.py:279-407: VisionTransformerInfer.forward returns softmax probabilities — against the
+    output of the reference's own get_video_vit_small model on the same weights and clips (fixture probs_ris)."""
+    from simple_tad_b200 import run_inference_simple as ris
+    g = parity.golden("c1_vits_b4")
+    model = ris.get_video_vit_small(with_flash=False)
+    model.load_state_dict(synth.make_state_dict("vit_small_patch16_224", seed=1), strict=True)
+    probs = model.to(DEV).eval()(synth.make_clips(4, seed=1).to(DEV))
+    assert probs.shape == (4, 2) and torch.allclose(probs.sum(-1).cpu(), torch.ones(4), atol=1e-5)
+    dp = float((probs.cpu() - torch.from_numpy(g["probs_ris"])).abs().max())
+    assert dp <= parity.TOL_DP, f"VisionTransformerInfer: max|dp| vs run_inference_simple = {dp:.3e}"
+
+
 def test_config2_vitb_sliding_window_video():
     """BASELINE config 2: ViT-B/16, one DoTA-shaped 100-frame video -> 85 stride-1 windows, per-frame scores.
     The windows are read straight out of the resident frame buffer (no clip materialisation)."""
