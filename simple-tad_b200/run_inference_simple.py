@@ -25,7 +25,7 @@ from .runner import IMAGENET_MEAN, IMAGENET_STD, StreamingScorer
 IMG_EXT = (".png", ".jpg", ".jpeg", ".JPG", ".JPEG")   # ris:15
 
 __all__ = ["IMG_EXT", "prepare_image", "VisionTransformerInfer", "get_video_vit_small", "get_video_vit_base",
-           "score_frame_folder", "main"]
+           "iter_frame_folder", "score_frame_folder", "main"]
 
 
 def prepare_image(img, mean, std, inplace=True):
@@ -70,7 +70,13 @@ def _natural_key(name):
 
 
 def score_frame_folder(model, frames_folder, size=(224, 224)):
-    """The loop of ris:428-463 as a generator of (frame index, risk probability).
+    """The loop of ris:428-463 as a generator of (frame index, risk probability)."""
+    for i, _, probs in iter_frame_folder(model, frames_folder, size):
+        yield i, float(probs[1])
+
+
+def iter_frame_folder(model, frames_folder, size=(224, 224)):
+    """The loop of ris:428-463 / run_inference.py:69-109 as a generator of (frame index, logits [2], probs [2]).
 
     The reference fills the window with the first 16 images, predicts, and then — `if i < 16: continue`, ris:447-448 —
     SKIPS the next 16 images entirely (they never enter the window) before it appends one image per prediction; the
@@ -88,12 +94,12 @@ def score_frame_folder(model, frames_folder, size=(224, 224)):
     out = None
     for name in names[:16]:
         out = scorer.push(read(name))
-    yield 15, float(out[1][1])                                   # "First prediction", ris:443-444
+    yield 15, out[0], out[1]                                     # "First prediction", ris:443-444
     for i, name in enumerate(names[16:]):
         if i < 16:                                               # ris:447-448
             continue
         out = scorer.push(read(name))
-        yield i, float(out[1][1])                                # ris:461-462 prints the loop index
+        yield i, out[0], out[1]                                  # ris:461-462 prints the loop index
 
 
 def main(ckpt_file, frames_folder):

@@ -237,3 +237,35 @@ def test_run_inference_simple_dropin_structure():
     with pytest.raises(TypeError):
         ris.prepare_image(img[:, :, 0], (0.5,), (0.5,))
     assert sorted(["f10.png", "f2.png", "f1.png"], key=ris._natural_key) == ["f1.png", "f2.png", "f10.png"]
+
+
+def test_frame_folder_loop_feeds_the_window_like_the_reference(tmp_path, monkeypatch):
+    """run_inference_simple.py:428-463 / run_inference.py:69-109: the first 16 images fill the window, the next 16 are
+    skipped (`if i < 16: continue`), then one image per prediction, reported under the loop index."""
+    import cv2
+    import numpy as np
+    from simple_tad_b200 import run_inference_simple as ris
+    for k in range(40):
+        cv2.imwrite(str(tmp_path / f"frame_{k}.png"), np.full((224, 224, 3), k, dtype=np.uint8))
+    (tmp_path / "notes.txt").write_text("not an image")
+    pushed = []
+
+    class _Scorer:
+        H, W = 224, 224
+
+        def __init__(self, model, **kw):
+            assert kw["bgr"] is True
+
+        def push(self, frame):
+            assert frame.dtype == torch.uint8 and tuple(frame.shape) == (224, 224, 3)
+            pushed.append(int(frame[0, 0, 0]))
+            if len(pushed) < 16:
+                return None
+            v = float(pushed[-1])
+            return torch.tensor([0.0, v]), torch.tensor([1.0 - v / 100.0, v / 100.0])
+
+    monkeypatch.setattr(ris, "StreamingScorer", _Scorer)
+    got = list(ris.score_frame_folder(object(), str(tmp_path)))
+    assert pushed == list(range(16)) + list(range(32, 40))          # natural order: frame_2 before frame_10
+    assert [i for i, _ in got] == [15] + list(range(16, 24))
+    assert got[0][1] == pytest.approx(0.15) and got[1][1] == pytest.approx(0.32) and got[-1][1] == pytest.approx(0.39)
