@@ -222,7 +222,6 @@ def main():
         entry.build()
     if world > 1:
         dist.barrier()
-    from functools import partial
     import synth_data as synth  # synthetic weights / inputs (repo-level module, not part of oracle/)
     from simple_tad_b200 import _lib, modeling_finetune as mf
     from simple_tad_b200.runner import SlidingWindowRunner, gather_scores

@@ -12,7 +12,6 @@ ABI (include/stad.h).  Inference only (eval mode, no autograd); there is no PyTo
     VisionTransformer  -> stad_vit_forward          (whole forward sequenced in C++, one ctypes call)
 """
 import ctypes as C
-import math
 from functools import partial
 
 import numpy as np
