@@ -360,7 +360,7 @@ def gen_variant(name):
 SEQ_CASES = [  # (timesteps_nb, input_frequency, seq_frequency, seq_length, step)
     (100, 10, 10, 16, 1), (16, 10, 10, 16, 1), (15, 10, 10, 16, 1), (100, 10, 10, 16, 10), (103, 10, 10, 16, 7),
     (150, 30, 10, 16, 1), (150, 30, 10, 16, 3), (151, 30, 10, 16, 10), (46, 30, 10, 16, 1), (45, 30, 10, 16, 1),
-    (90, 30, 10, 8, 10), (64, 20, 10, 8, 5), (200, 30, 30, 16, 4),
+    (90, 30, 10, 8, 10), (64, 20, 10, 8, 5), (200, 30, 30, 16, 4), (107, 10, 10, 16, 10), (159, 30, 10, 16, 20),
 ]
 
 
@@ -375,7 +375,9 @@ def gen_sequences(name):
     for i, (T, fin, fseq, length, step) in enumerate(SEQ_CASES):
         seqs = mod.RegularSequencer(seq_frequency=fseq, seq_length=length, step=step).get_sequences(T, fin)
         out[f"seq_{i}"] = np.zeros((0, length), dtype=np.int64) if seqs is None else np.array(seqs, dtype=np.int64)
-        print(f"  {SEQ_CASES[i]}: {0 if seqs is None else len(seqs)} windows")
+        ws = mod.RegularSequencerWithStart(seq_frequency=fseq, seq_length=length, step=step).get_sequences(T, fin)
+        out[f"seqws_{i}"] = np.zeros((0, length), dtype=np.int64) if ws is None else np.array(ws, dtype=np.int64)
+        print(f"  {SEQ_CASES[i]}: {0 if seqs is None else len(seqs)} windows (+{0 if ws is None else len(ws) - len(seqs)} with start)")
     save(name, **out)
 
 

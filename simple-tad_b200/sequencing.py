@@ -51,3 +51,17 @@ def window_plan(timesteps_nb, input_frequency=10, seq_frequency=10, seq_length=1
     count = (timesteps_nb - span) // step + 1
     start = (timesteps_nb - span) % step
     return WindowPlan(start, count, step, frame_step, seq_length)
+
+
+def window_plan_with_start(timesteps_nb, input_frequency=10, seq_frequency=10, seq_length=16, step=1):
+    """RegularSequencerWithStart (dataset/sequencing.py:132-167; the DAPT video datasets, dota.py:555): the plan of
+    window_plan plus, when end alignment leaves more than min(0.3 * input_frequency, 5) frames unused at the start of the
+    video, ONE extra window that begins at frame 0 (the reference appends it after the regular ones).
+    Returns (plan, extra) with extra = WindowPlan(start=0, count=1, ...) or None; (None, None) for a too-short video."""
+    plan = window_plan(timesteps_nb, input_frequency, seq_frequency, seq_length, step)
+    if plan is None:
+        return None, None
+    extra = None
+    if plan.start > min(0.3 * input_frequency, 5):
+        extra = WindowPlan(0, 1, plan.stride, plan.frame_step, plan.length)
+    return plan, extra

@@ -25,6 +25,23 @@ def test_window_plan_reproduces_regular_sequencer():
         assert total == plan.count and segs == [(0, 0, plan.count)]
 
 
+def test_window_plan_with_start_reproduces_the_reference():
+    """RegularSequencerWithStart (dataset/sequencing.py:132-167): the regular windows, then one window from frame 0 when
+    the end-aligned windows leave the first frames uncovered."""
+    g = parity.golden("sequencer")
+    extras = 0
+    for i, (T, fin, fseq, length, step) in enumerate(g["cases"].tolist()):
+        ref = g[f"seqws_{i}"]
+        plan, extra = sequencing.window_plan_with_start(T, fin, fseq, length, step)
+        if ref.shape[0] == 0:
+            assert plan is None and extra is None
+            continue
+        seqs = plan.sequences() + (extra.sequences() if extra is not None else [])
+        assert np.array_equal(np.array(seqs), ref), (T, fin, fseq, length, step)
+        extras += extra is not None
+    assert extras >= 2   # the grid holds cases on both sides of the min(0.3 * fps, 5) rule
+
+
 def test_window_plan_arguments():
     assert sequencing.window_plan(range(100)).count == 85                 # a sequence of timesteps (sequencing.py:43-44)
     assert sequencing.window_plan(100, seq_length=1.6).length == 16       # seconds (sequencing.py:11-14)
