@@ -293,6 +293,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
           ATT_EV(2 + slot, 20);
           if (elect_one()) {
             const uint64_t desc_k = make_smem_desc_sw128(smem_u32(smem_k + kst * TILE_BYTES), 16, 1024);
+#ifdef STAD_ATT_NO_MMA
+            // development build (-DSTAD_ATT_NO_MMA, tools/build_variant.sh): the barrier protocol runs, the tensor core
+            // does not (results are garbage).  Splits the cost of the hand-overs from the cost of sharing TMEM / the SM
+            // with the MMAs.
+            (void)desc_k;
+            (void)cols;
+#else
             if (cols == BKV) {
 #pragma unroll
               for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc_qk_full, k != 0);
@@ -301,6 +308,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
 #pragma unroll
               for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc, k != 0);
             }
+#endif
             ATT_EV(2 + slot, 21);
             umma_commit(&s_full[slot]);
             if (last_of_unit) umma_commit(&q_free[slot]);
@@ -318,6 +326,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
           ATT_EV(2 + slot, 22);
           if (elect_one()) {
             const uint64_t desc_v = make_smem_desc_sw128(smem_u32(smem_v + vst * TILE_BYTES), 0, 1024);
+#ifdef STAD_ATT_NO_MMA
+            (void)desc_v;
+            (void)accumulate;
+            (void)ksteps;
+#else
             if (ksteps == BKV / 16) {
 #pragma unroll
               for (int k = 0; k < BKV / 16; ++k)
@@ -326,6 +339,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_cons
               for (int k = 0; k < ksteps; ++k)
                 umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
             }
+#endif
             ATT_EV(2 + slot, 23);
             umma_commit(&o_full[slot]);
             umma_commit(&v_free[vst]);
