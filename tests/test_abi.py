@@ -100,3 +100,48 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle/"
+
+
+def test_argument_errors_are_reported_before_any_device_work(lib):
+    """Error convention of the boundary: bad shapes / alignment return STAD_E_SHAPE / STAD_E_ALIGN with a
+    message and are mapped to ValueError — decided on the host, so this holds without a GPU."""
+    l = lib.load()
+    buf = (ctypes.c_uint8 * 256)()
+    addr = (ctypes.addressof(buf) + 15) & ~15          # 16-byte aligned host address standing in for a device pointer
+    p, odd = ctypes.c_void_p(addr), ctypes.c_void_p(addr + 2)
+    # rows_norm_head: empty problem, misaligned rows, a head without logits
+    assert l.stad_rows_norm_head(p, p, p, p, p, p, None, None, 0, 1, 0, 768, 2, 1e-6, None) == lib.STAD_E_SHAPE
+    assert l.stad_rows_norm_head(odd, p, p, p, p, p, None, None, 4, 1, 0, 768, 2, 1e-6, None) == lib.STAD_E_ALIGN
+    assert l.stad_rows_norm_head(p, p, p, p, p, None, None, None, 4, 1, 0, 768, 2, 1e-6, None) == lib.STAD_E_SHAPE
+    assert "rows_norm_head" in lib.last_error()
+    assert l.stad_rows_norm_head(p, p, p, p, p, p, None, None, 4, 0, 0, 768, 2, 1e-6, None) == lib.STAD_E_SHAPE
+    # prepend_cls: empty batch, width that is not a multiple of 8
+    assert l.stad_prepend_cls(p, p, p, p, 0, 1568, 768, 1e-6, None) == lib.STAD_E_SHAPE
+    assert l.stad_prepend_cls(p, p, p, p, 2, 1568, 770, 1e-6, None) == lib.STAD_E_SHAPE
+    # frame-buffer input: the last clip must fit the resident frames, also with an in-window frame step
+    dims = lib.make_dims(dim=384, depth=1, heads=6, hidden=1536, num_classes=2)
+    ok = lib.StadInput(addr, lib.STAD_IN_FRAMES, 46 + 5, 0, 5, 3)    # 2 clips: (16 - 1) * 3 + 1 = 46 frames each, 5 apart
+    short = lib.StadInput(addr, lib.STAD_IN_FRAMES, 46 + 4, 0, 5, 3)
+    rc = l.stad_patch_embed(ctypes.byref(short), p, p, None, p, None, ctypes.byref(dims), 2, 1568, None)
+    assert rc == lib.STAD_E_SHAPE and "needs frame 50" in lib.last_error()
+    neg = lib.StadInput(addr, lib.STAD_IN_FRAMES, 100, 0, 1, -1)
+    assert l.stad_patch_embed(ctypes.byref(neg), p, p, None, p, None, ctypes.byref(dims), 2, 1568, None) == lib.STAD_E_SHAPE
+    with pytest.raises(ValueError, match="frame_step"):
+        lib.check(l.stad_patch_embed(ctypes.byref(neg), p, p, None, p, None, ctypes.byref(dims), 2, 1568, None), "patch_embed")
+    del ok
+    # vit_forward: unknown reduction, class token together with a visible-token list
+    m = lib.StadModel()
+    m.dims = dims
+    blocks = (lib.StadBlock * 1)()
+    m.blocks = ctypes.cast(blocks, ctypes.POINTER(lib.StadBlock))
+    m.norm_g = m.norm_b = m.w_head = m.b_head = addr
+    m.reduction = 7
+    outs = lib.StadOutputs(addr, None, None, None)
+    inp = lib.StadInput(addr, lib.STAD_IN_CLIPS, 0, 0, 1, 1)
+    ws = ctypes.c_void_p((addr + 255) & ~255)
+    rc = l.stad_vit_forward(ctypes.byref(m), ctypes.byref(inp), None, 1, 1568, ctypes.byref(outs), ws, 1 << 40, None)
+    assert rc == lib.STAD_E_SHAPE and "reduction" in lib.last_error()
+    m.reduction = lib.STAD_REDUCE_MEAN
+    m.cls_token = addr
+    rc = l.stad_vit_forward(ctypes.byref(m), ctypes.byref(inp), p, 1, 160, ctypes.byref(outs), ws, 1 << 40, None)
+    assert rc == lib.STAD_E_SHAPE and "class token" in lib.last_error()
