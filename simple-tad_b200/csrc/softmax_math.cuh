@@ -24,11 +24,12 @@ STAD_DEVICE float ex2(float x) {
 
 // 2^x for a pair, entirely on the FMA/ALU pipes: x = n + f, n = round(x), f in [-0.5, 0.5];
 // 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far below bf16 resolution of P), n added to the
-// exponent field.  x is clamped at -125 so the exponent never wraps.
+// exponent field.  x is clamped to [-125, 127] so the exponent never wraps (the attention kernel's lazy reference max
+// allows positive arguments; 2^127 trips its row-sum guard).
 STAD_DEVICE void exp2_poly2(float& e0, float& e1, float x0, float x1) {
   constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: x + kMagic holds round(x) in its low mantissa bits
-  x0 = fmaxf(x0, -125.f);
-  x1 = fmaxf(x1, -125.f);
+  x0 = fminf(fmaxf(x0, -125.f), 127.f);
+  x1 = fminf(fmaxf(x1, -125.f), 127.f);
   float r0, r1, n0, n1, f0, f1, p0, p1;
   add2(r0, r1, x0, x1, kMagic, kMagic);
   add2(n0, n1, r0, r1, -kMagic, -kMagic);

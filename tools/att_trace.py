@@ -11,8 +11,8 @@ CAP = 2048
 buf = (C.c_ulonglong * (4 * CAP))(); cnt = (C.c_int * 4)()
 L.attention(qkv); torch.cuda.synchronize(); lib.stad_debug_read_att_trace(buf, cnt)
 L.attention(qkv); torch.cuda.synchronize(); lib.stad_debug_read_att_trace(buf, cnt)
-TAGS = {7: "loop top", 0: "s_full ok", 1: "S in regs,s_free", 2: "max done", 8: "chunk0 done", 9: "o_full ok", 3: "exps+st issued", 4: "ld issued", 5: "p_full arrived",
-        10: "mma: wait s_free", 11: "mma: s_free ok", 12: "mma: QK issued", 13: "mma: p_full ok", 14: "mma: PV issued", 20: "mma: k_full ok", 21: "mma: QK mmas issued", 22: "mma: v_full ok", 23: "mma: PV mmas issued"}
+TAGS = {7: "tile top", 0: "s_full ok", 1: "S in regs", 3: "exps+st issued", 5: "p_full arrived",
+        20: "mma: k_full ok", 21: "mma: QK issued", 22: "mma: v_full ok", 23: "mma: p_full ok", 24: "mma: PV issued"}
 ev = []
 for role in ([2] if len(sys.argv) > 3 else range(4)):
     for i in range(cnt[role]):

@@ -1,0 +1,39 @@
+"""Small-shape workload for compute-sanitizer (racecheck / synccheck / memcheck) over the mbarrier-heavy kernels:
+single-CTA and CTA-pair GEMM tiles with every epilogue, and the attention kernel with two-slot, one-slot, ragged and
+key-split units.  Results are still checked against PyTorch fp32 (tests/kernel_checks.py), so a sanitizer-clean run
+is also a correct run.
+    compute-sanitizer --tool racecheck python tools/sanitize_small.py [gemm|pair|attention|rows]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from tests import kernel_checks as kc  # noqa: E402
+
+GROUPS = {
+    "gemm": lambda: [kc.check_gemm(300, 192, 128, "bias", seed=1), kc.check_gemm(256, 256, 256, "resid", seed=2),
+                     kc.check_gemm(200, 384, 384, "ln", seed=3), kc.check_gemm(257, 512, 128, "ln_gelu", seed=4),
+                     kc.check_gemm_stats(384, 384, 256, 128, seed=5)],
+    # pair tiles need N % 256 == 0 and >= 74 pair tiles: 9472 x 512 -> 37 x 2 pair tiles; K kept small
+    "pair": lambda: [kc.check_gemm(9472, 512, 2048, "bias", seed=6), kc.check_gemm(9600, 768, 768, "resid", seed=7),
+                     kc.check_gemm(9472, 1024, 768, "ln_gelu", seed=8), kc.check_gemm_stats(9472, 768, 512, 768, seed=9)],
+    "attention": lambda: [kc.check_attention(1, 2, 288, seed=1), kc.check_attention(1, 1, 160, seed=2),
+                          kc.check_attention(2, 1, 100, seed=3), kc.check_attention(1, 1, 417, peaky=4.0, seed=4),
+                          kc.check_attention(40, 4, 160, seed=5)],
+    "rows": lambda: [kc.check_pool_head(3, 160, 384), kc.check_layernorm(100, 768), kc.check_row_stats(100, 384),
+                     kc.check_normalize_u8(2, 64, 64), kc.check_decoder_assemble(2, 196, 20, 192, seed=50)],
+}
+
+
+def main():
+    names = sys.argv[1:] or list(GROUPS)
+    for n in names:
+        GROUPS[n]()
+        torch.cuda.synchronize()
+        print(f"sanitize_small: {n} ok", flush=True)
+
+
+if __name__ == "__main__":
+    main()
