@@ -118,10 +118,6 @@ STAD_DEVICE Unit decode_unit(int u, int units_per_head, int H, int S) {
   return w;
 }
 
-STAD_DEVICE void fill_neg_inf(uint32_t (&t)[32]) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) t[i] = 0xFF800000u;
-}
 STAD_DEVICE void mask_from(uint32_t (&t)[32], int valid) {  // columns >= valid -> -inf
 #pragma unroll
   for (int i = 0; i < 32; ++i)
@@ -177,7 +173,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 4);  // one arrive per softmax warp
+      mbar_init(&p_full[s], BQ);  // one arrive per softmax thread
     }
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
@@ -482,11 +478,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tmem_st32(o_addr + q * 32, ov);
       }
     };
-    auto publish_p = [&](uint32_t buf) {  // my P columns of this tile are in TMEM: let the issuer run P V
+    // Barrier addresses as plain 32-bit shared addresses, computed once.
+    const uint32_t s_full_a = smem_u32(&s_full[slot * 2]);
+    const uint32_t p_full_a = smem_u32(&p_full[slot * 2]);
+    // My P columns of this tile are in TMEM: let the issuer run P V.  EVERY thread arrives (the barrier counts the 128
+    // threads of the slot): no warp barrier, no elected lane, no branch on the way out of the tile.
+    auto publish_p = [&](uint32_t p_bar) {
       tmem_st_wait();
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[slot * 2 + buf]);
+      mbar_arrive_a(p_bar);
     };
 
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
@@ -538,7 +538,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (q == quarter) tmem_st16(sp + q * 16, pk);
             else tmem_st16(sp + q * 16, z);
           }
-          publish_p(buf);
+          publish_p(p_full_a + buf * 8);
         }
         lsum_smem[r] = l_sum;        // partial sum of (query lane, key part)
         lsum_smem[BQ + r] = m_ref;   // its reference max (-inf: this part never saw a key); slot 1's half is idle here
@@ -546,36 +546,49 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         continue;
       }
       const int row0 = w.q0 + slot * BQ;
-      const bool warp_valid = row0 + quarter * 32 < p.S;  // warp-uniform: any valid query row in this warp
-      float m_ref = 0.f;  // reference max (log2 domain, already scaled): exact max of the unit's first tile
-      float l_sum = 0.f;
-
-      for (int j = 0; j < n_kv; ++j, ++g) {
-        const uint32_t buf = g & 1;
-        const uint32_t sp = slot_addr + buf * BKV;
-        ATT_T(7);
-        // Phase offset between the two slots, re-established at the first tile of every two-slot unit: without it both
-        // softmax warpgroups drift into lockstep (same phase of the tile at the same time), i.e. they fight for the
-        // MUFU together and idle together.  Slot 1 starts when slot 0 has stored the first third of its first P tile.
-        const bool stagger = STAD_ATT_STAGGER && j == 0 && w.slots == 2;
+      // Phase offset between the two slots, re-established at the first tile of every two-slot unit: without it both
+      // softmax warpgroups drift into lockstep (same phase of the tile at the same time), i.e. they fight for the
+      // MUFU together and idle together.  Slot 1 starts when slot 0 has stored the first third of its first P tile.
+      const bool stagger = STAD_ATT_STAGGER && w.slots == 2;
+      // loop-carried tile state, toggled instead of re-derived from g (keeps the per-tile glue short): score buffer
+      // address (the two buffers differ in one address bit pattern: BKV = 0x60 and the slot base has those bits clear),
+      // barrier addresses (8 bytes apart, 16-byte aligned pairs), barrier phase
+      uint32_t buf = g & 1;
+      uint32_t sp = slot_addr + buf * BKV;
+      uint32_t s_bar = s_full_a + buf * 8, p_bar = p_full_a + buf * 8;
+      uint32_t ph = (g >> 1) & 1;
+      if (row0 + quarter * 32 >= p.S) {
+        // rows beyond S (warp-uniform): nothing to compute (their P / O rows are never stored); keep the pipeline
+        // moving.  (The previous phase of p_full[buf] is complete: Q K_j^T was issued after P_{j-2} V_{j-2}.)
         if (stagger) {
           if (slot == 1) named_bar_sync(1, 2 * BQ);
-          else if (!warp_valid) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+          else asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
         }
-        mbar_wait(&s_full[slot * 2 + buf], (g >> 1) & 1);
-        if (!warp_valid) {
-          // rows beyond S: nothing to compute (their P / O rows are never stored); keep the pipeline moving.  (The
-          // previous phase of p_full[buf] is complete: Q K_j^T was issued after P_{j-2} V_{j-2}.)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[slot * 2 + buf]);
-          continue;
+        for (int j = 0; j < n_kv; ++j, ++g) {
+          mbar_wait_a(s_bar, ph);
+          mbar_arrive_a(p_bar);
+          ph ^= buf;
+          buf ^= 1;
+          s_bar ^= 8;
+          p_bar ^= 8;
         }
+        lsum_smem[slot * BQ + r] = 1.f;
+        mbar_arrive(&l_ready[slot]);
+        continue;
+      }
+      float m_ref = 0.f;  // reference max (log2 domain, already scaled): exact max of the unit's first tile
+      float l_sum = 0.f;
+      const int n_full = (last_valid == BKV) ? n_kv : n_kv - 1;  // tiles with all 96 keys valid
+
+      for (int j = 0; j < n_kv; ++j, ++g, ph ^= buf, buf ^= 1, sp ^= BKV, s_bar ^= 8, p_bar ^= 8) {
+        ATT_T(7);
+        if (j == 0 && stagger && slot == 1) named_bar_sync(1, 2 * BQ);
+        mbar_wait_a(s_bar, ph);
         tc_fence_after();
         ATT_T(0);
-        const int ncols = (j + 1 < n_kv) ? BKV : last_valid;  // valid keys of this tile
         uint32_t sv[3][32];
         float t_sum;
-        if (j > 0 && ncols == BKV) {
+        if (j > 0 && j < n_full) {
           // ---- steady state: full tile, lazy reference.  The second and third chunk are in flight while the first
           // is processed; P chunk i overwrites columns [16 i, +16), which lie in S chunk i / 2 (already in registers).
           const float neg_m = -m_ref;
@@ -598,6 +611,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           ATT_T(3);
         } else {
           // ---- first tile of the unit (exact max -> reference) and / or ragged last tile (masked, fewer chunks)
+          const int ncols = (j + 1 < n_kv) ? BKV : last_valid;  // valid keys of this tile
           const int nch = (ncols + 31) >> 5;
 #pragma unroll
           for (int q = 0; q < 3; ++q)
@@ -608,7 +622,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               tmem_ld_wait32(sv[q]);
               if (ncols - q * 32 < 32) mask_from(sv[q], ncols - q * 32);
             } else {
-              fill_neg_inf(sv[q]);
+              mask_from(sv[q], 0);
             }
           }
           if (j == 0) m_ref = c * max3(chunk_max(sv[0]), chunk_max(sv[1]), chunk_max(sv[2]));
@@ -620,7 +634,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               uint32_t pk[16];
               exp_chunk<false>(sv[q], c, neg_m, a0, a1, pk);
               tmem_st16(sp + q * 16, pk);
-              if (q == 0 && stagger && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+              if (q == 0 && j == 0 && stagger && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
             }
           }
           t_sum = a0 + a1;
@@ -651,7 +665,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
         }
         l_sum += t_sum;
-        publish_p(buf);
+        publish_p(p_bar);
         ATT_T(5);
       }
       // ---- hand the row sum to the epilogue warps and go on with the next unit

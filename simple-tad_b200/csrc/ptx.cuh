@@ -69,6 +69,30 @@ STAD_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// the same three on a precomputed 32-bit shared address (hot loops: no generic -> shared conversion per call)
+STAD_DEVICE void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+STAD_DEVICE bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+STAD_DEVICE void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_a(bar, parity)) {
+    if (++spins > STAD_WAIT_SPIN_LIMIT) __trap();
+  }
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // pdl_wait: block until the kernel before this one in the stream has completed and its writes are visible (no-op when
 // the kernel was not launched with the programmatic-serialization attribute).  pdl_launch_dependents: let the next
