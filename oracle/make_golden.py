@@ -66,18 +66,19 @@ def install_shims():
         sys.path.insert(0, REF)
 
 
-def ref_classifier(arch, sd):
+def ref_classifier(arch, sd, init_values=0.0):
     """The reference VisionTransformer (modeling_finetune.py) in fp32 with the naive attention path."""
     import modeling_finetune as mf
     from functools import partial
     D, depth, heads = synth.ARCHS[arch]
-    if arch in mf.__dict__:
+    if arch in mf.__dict__ and init_values == 0.0:
         model = mf.__dict__[arch](num_classes=2, all_frames=16, tubelet_size=2, use_flash_attn=False, init_scale=1.0,
                                   final_reduction="fc_norm")
     else:  # reduced-depth variant: same ctor the factories call (mf:340-342), only `depth` differs
         model = mf.VisionTransformer(patch_size=16, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
                                      norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=2, all_frames=16,
-                                     tubelet_size=2, use_flash_attn=False, init_scale=1.0, final_reduction="fc_norm")
+                                     tubelet_size=2, use_flash_attn=False, init_scale=1.0, final_reduction="fc_norm",
+                                     init_values=init_values)
     missing = model.load_state_dict(sd, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
     return model.eval()
@@ -122,14 +123,16 @@ def save(name, **arrs):
     print(f"  wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
 
 
-def gen_classifier(name, arch, B=None, video_T=None, n_videos=1, seed=0, peaky=1.0, use_ris=False, check_oracle=True):
+def gen_classifier(name, arch, B=None, video_T=None, n_videos=1, seed=0, peaky=1.0, use_ris=False, check_oracle=True,
+                   trained_like=False):
     D, depth, heads = synth.ARCHS[arch]
-    sd = synth.make_state_dict(arch, seed=seed, peaky=peaky)
+    sd = (synth.make_trained_like_state_dict(arch, seed=seed) if trained_like else
+          synth.make_state_dict(arch, seed=seed, peaky=peaky))
     if video_T is None:
         x = synth.make_clips(B, seed=seed)
     else:
         x = torch.cat([synth.windows_from_video(synth.make_video(video_T, seed=seed + v)) for v in range(n_videos)])
-    model = ref_classifier(arch, sd)
+    model = ref_classifier(arch, sd, init_values=0.1 if trained_like else 0.0)
     t0 = time.time()
     logits, hs = [], None
     for i in range(0, x.shape[0], 4):
@@ -413,6 +416,11 @@ def main():
         gen_pretrain("c4_mae_vitb_b2", "vit_base_patch16_224", B=2, seed=6, decoder_depth=4)
     if on("c5"):
         gen_classifier("c5_vitb_b8", "vit_base_patch16_224", B=8, seed=5)
+    if on("trained"):
+        # trained-like statistics (outlier channels, shifted rows, wide LayerNorm gamma, layer scale): see
+        # synth.make_trained_like_state_dict
+        gen_classifier("trained_vits_d2_b2", "vit_small_d2", B=2, seed=31, trained_like=True)
+        gen_classifier("trained_vitb_b4", "vit_base_patch16_224", B=4, seed=32, trained_like=True)
     if on("sequencer"):
         gen_sequences("sequencer")
     for name in VARIANTS:

@@ -50,12 +50,13 @@ def mlp(sd, p, x):
 
 
 def block(sd, i, x, heads):
-    """Block.forward with gamma_1 None (init_values=0), mf:159-162."""
+    """Block.forward, mf:159-166: without layer scale (gamma_1 None, init_values = 0) or with it (mf:164-165)."""
     p = f"blocks.{i}."
     D = x.shape[-1]
-    x = x + attention(sd, p, F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], LN_EPS), heads)
-    x = x + mlp(sd, p, F.layer_norm(x, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], LN_EPS))
-    return x
+    a = attention(sd, p, F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], LN_EPS), heads)
+    x = x + (sd[p + "gamma_1"] * a if p + "gamma_1" in sd else a)
+    m = mlp(sd, p, F.layer_norm(x, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], LN_EPS))
+    return x + (sd[p + "gamma_2"] * m if p + "gamma_2" in sd else m)
 
 
 def _depth(sd):

@@ -88,6 +88,38 @@ def make_state_dict(arch, seed=0, num_classes=2, encoder=False, peaky=1.0):
     return sd
 
 
+OUTLIER_CHANNELS = (7, 123, 300)  # valid for every width in ARCHS
+
+
+def make_trained_like_state_dict(arch, seed=0, num_classes=2, init_values=0.1):
+    """Weights with the statistics of a TRAINED video ViT rather than of trunc-normal init — the regime where a bf16
+    residual stream and LayerNorm statistics taken from E[x^2] - mean^2 partial sums could lose accuracy:
+      * massive-activation channels: three channels of the residual stream sit 60-100 x above the typical |x| (the
+        patch-embed bias puts them there, the fc2 biases of the first blocks keep feeding them);
+      * token rows with a mean of several sigma (every channel of the patch-embed bias is shifted);
+      * LayerNorm gamma spread log-uniformly over [0.1, 5] and beta ~ 0.3 N(0, 1) in every block;
+      * layer scale (init_values > 0): gamma_1 / gamma_2 = init_values (1 + 0.3 N(0, 1)), modeling_finetune.py:153-162.
+    The head and fc_norm keep make_state_dict's scale so that the probabilities stay informative."""
+    D, depth, _ = ARCHS[arch]
+    sd = make_state_dict(arch, seed=seed, num_classes=num_classes)
+    g = _gen(9000 + seed)
+    ch = torch.tensor(OUTLIER_CHANNELS)
+    sign = torch.tensor([1.0, -1.0, 1.0])
+    sd["patch_embed.proj.bias"] = sd["patch_embed.proj.bias"] + 1.5
+    sd["patch_embed.proj.bias"][ch] += sign * (40.0 + 20.0 * torch.rand((3,), generator=g))
+    lo, hi = math.log(0.1), math.log(5.0)
+    for i in range(depth):
+        p = f"blocks.{i}."
+        for n in ("norm1", "norm2"):
+            sd[p + n + ".weight"] = torch.exp(lo + (hi - lo) * torch.rand((D,), generator=g))
+            sd[p + n + ".bias"] = 0.3 * torch.randn((D,), generator=g)
+        if i < 2:
+            sd[p + "mlp.fc2.bias"][ch] += sign * (100.0 + 50.0 * torch.rand((3,), generator=g))
+        sd[p + "gamma_1"] = init_values * (1.0 + 0.3 * torch.randn((D,), generator=g))
+        sd[p + "gamma_2"] = init_values * (1.0 + 0.3 * torch.randn((D,), generator=g))
+    return sd
+
+
 def make_variant_state_dict(arch, seed=0, num_classes=2, tubelet=TUBELET, final_reduction="fc_norm", cls_token=False):
     """make_state_dict re-keyed for the other forms of the classifier: final_reduction 'cls' / 'none' own `norm.*`
     instead of `fc_norm.*` (modeling_finetune.py:269-270); tubelet 1 (the UMT job) keeps the first temporal slice of

@@ -47,6 +47,41 @@ def test_small_models_vs_reference_and_oracle_hidden(fixture, arch, seed, peaky)
         assert rel <= parity.TOL_HIDDEN_REL_L2, f"{fixture}: hidden state {i} rel-L2 {rel:.3e}"
 
 
+@pytest.mark.parametrize("fixture,arch,seed,B", [
+    ("trained_vits_d2_b2", "vit_small_d2", 31, 2),
+    ("trained_vitb_b4", "vit_base_patch16_224", 32, 4),
+])
+def test_trained_like_statistics(fixture, arch, seed, B):
+    """Weights with the statistics of a TRAINED model (synth.make_trained_like_state_dict): residual-stream channels
+    60-100 x above the typical magnitude, row means of several sigma, LayerNorm gamma in [0.1, 5], layer scale
+    init_values = 0.1 (mf:153-165).  This is where a bf16 residual stream and LayerNorm statistics from E[x^2] - mean^2
+    partial sums would break first.  Logits against the unmodified reference (BASELINE tolerance) through the whole-model
+    path, hidden states per block against the fp32 oracle through the module path."""
+    from functools import partial
+    from simple_tad_b200 import modeling_finetune as mf
+    g = parity.golden(fixture)
+    sd = synth.make_trained_like_state_dict(arch, seed=seed)
+    x = synth.make_clips(B, seed=seed)
+    D, depth, heads = synth.ARCHS[arch]
+    model = mf.VisionTransformer(patch_size=16, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
+                                 norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=2, all_frames=16,
+                                 tubelet_size=2, init_scale=1.0, final_reduction="fc_norm", init_values=0.1)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    parity.check_logits(model(x.to(DEV)), g["logits"], fixture)
+    _, hid_ref = vit_oracle.vit_forward(sd, x[:2], heads, return_hidden=True)
+    hid = _hidden_states_gpu(model, x[:2].to(DEV))
+    for i, (a, b) in enumerate(zip(hid, hid_ref)):
+        a = a.float().cpu()
+        rel = float((a - b).norm() / b.norm())
+        assert rel <= parity.TOL_HIDDEN_REL_L2, f"{fixture}: hidden state {i} rel-L2 {rel:.3e}"
+        # the ordinary channels on their own (the outlier channels dominate the norm above)
+        keep = torch.ones(D, dtype=torch.bool)
+        keep[list(synth.OUTLIER_CHANNELS)] = False
+        rel_in = float((a[..., keep] - b[..., keep]).norm() / b[..., keep].norm())
+        assert rel_in <= parity.TOL_HIDDEN_REL_L2, f"{fixture}: hidden state {i}, ordinary channels, rel-L2 {rel_in:.3e}"
+
+
 def test_config1_vits_batch4():
     """BASELINE config 1: ViT-S/16, batch-4 synthetic clips, probabilities of run_inference_simple's model."""
     g = parity.golden("c1_vits_b4")

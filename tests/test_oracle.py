@@ -38,6 +38,25 @@ def test_small_classifier_logits_and_hidden(fixture, arch, seed, peaky):
     assert (np.abs(p - 0.5) > 0.02).all() and (p > 1e-3).all() and (p < 1 - 1e-3).all()
 
 
+@pytest.mark.parametrize("fixture,arch,seed,B", [("trained_vits_d2_b2", "vit_small_d2", 31, 2)])
+def test_trained_like_classifier_matches_the_reference(fixture, arch, seed, B):
+    """Trained-like statistics (outlier channels, shifted rows, wide LayerNorm gamma, layer scale): the oracle's Block
+    with gamma_1 / gamma_2 reproduces the unmodified reference (mf:153-165)."""
+    g = parity.golden(fixture)
+    sd = synth.make_trained_like_state_dict(arch, seed=seed)
+    x = synth.make_clips(B, seed=seed)
+    D, depth, heads = synth.ARCHS[arch]
+    logits, hid = vit_oracle.vit_forward(sd, x, heads, return_hidden=True)
+    assert float((logits - torch.from_numpy(g["logits"])).abs().max()) <= 1e-5
+    tok, ch = torch.from_numpy(g["hid_tok"]), torch.from_numpy(g["hid_ch"])
+    samp = torch.stack([h[:, tok][:, :, ch] for h in hid])
+    assert float((samp - torch.from_numpy(g["hidden_samples"])).abs().max()) <= 1e-4
+    # the fixture really has the statistics it is named for
+    out = hid[-1][0][:, list(synth.OUTLIER_CHANNELS)].abs().mean()
+    typ = hid[-1][0][:, 50].abs().mean()
+    assert out > 30 * typ
+
+
 def test_small_encoder_tokens():
     g = parity.golden("small_enc_vitb_d2_b2")
     D, depth, heads = synth.ARCHS["vit_base_d2"]
