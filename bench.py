@@ -38,6 +38,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64, help="windows (clips) per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-clips", type=int, default=1, help="--impl reference: clips per step (bounded sample)")
+    ap.add_argument("--preheat-s", type=float, default=2.5, help="untimed steps run for this long before the timed region "
+                                                                  "(the SM clock settles under the power cap)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-3 / config-5 legs (keys c3, c5)")
     return ap.parse_args()
 
 
@@ -128,19 +131,32 @@ def workload_config(model_name, B, world, sample=None):
 
 
 def cpu_forward_setup(model_name):
-    """The reference algorithm on the CPU (oracle/ = restatement of modeling_finetune.py pinned by tests/golden)."""
-    from oracle import synth, vit_oracle
+    """The reference's CPU forward: the UNMODIFIED modeling_finetune.VisionTransformer from oracle/_ref/ when the build
+    step put it there (kind "reference"), else oracle/vit_oracle.py, its restatement pinned by tests/golden (kind "port").
+    Returns (run(clips) -> logits, synth module, kind)."""
+    from oracle import ref_loader, synth, vit_oracle
     D, depth, heads = synth.ARCHS[model_name]
     sd = synth.make_state_dict(model_name, seed=0)
     torch.set_num_threads(os.cpu_count())
+    mf_ref = ref_loader.load()
+    if mf_ref is not None and model_name in mf_ref.__dict__:
+        model = mf_ref.__dict__[model_name](num_classes=2, all_frames=16, tubelet_size=2, use_flash_attn=False,
+                                            init_scale=1.0, final_reduction="fc_norm")
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+
+        @torch.no_grad()
+        def run_ref(clips):
+            return model(clips)
+        return run_ref, synth, "reference"
 
     def run(clips):
         return vit_oracle.vit_forward(sd, clips, heads)
-    return run, synth
+    return run, synth, "port"
 
 
 def cpu_baseline(model_name, clips=2, repeats=2):
-    run, synth = cpu_forward_setup(model_name)
+    run, synth, kind = cpu_forward_setup(model_name)
     x = synth.make_clips(clips, seed=123)
     run(x[:1])  # warm-up (thread pool, oneDNN primitives)
     best = float("inf")
@@ -148,18 +164,20 @@ def cpu_baseline(model_name, clips=2, repeats=2):
         t0 = time.perf_counter()
         run(x)
         best = min(best, time.perf_counter() - t0)
-    return {"value": clips / best, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"best of {repeats} fp32 forwards of {clips} synthetic clips ({model_name}) through oracle/vit_oracle.py "
+    what = ("the unmodified reference modeling_finetune.py (oracle/_ref)" if kind == "reference" else
+            "oracle/vit_oracle.py (the port)")
+    return {"value": clips / best, "unit": "clips/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": f"best of {repeats} fp32 forwards of {clips} synthetic clips ({model_name}) through {what} "
                       f"(torch {torch.__version__} CPU, {torch.get_num_threads()} threads)"}
 
 
 def run_reference(args, rank, world, out):
-    """--impl reference: the reference's own CPU implementation of the path.  The reference is pure Python and is not
-    present on the GPU box, so this times oracle/ (its restatement, checked against the reference's outputs in
-    tests/golden).  Rank 0 alone runs it."""
+    """--impl reference: the reference's own CPU implementation of the path — the unmodified modeling_finetune.py copied
+    into oracle/_ref/ by the build step (it travels to the GPU box with the snapshot), else oracle/ (its restatement,
+    checked against the reference's outputs in tests/golden).  Rank 0 alone runs it."""
     if rank != 0:
         return
-    run, synth = cpu_forward_setup(args.model)
+    run, synth, kind = cpu_forward_setup(args.model)
     x = synth.make_clips(args.ref_clips, seed=123)
     for _ in range(max(1, min(args.warmup, 2))):
         run(x)
@@ -175,13 +193,74 @@ def run_reference(args, rank, world, out):
         "config": workload_config(args.model, args.batch, args.gpus,
                                   sample=f"bounded sample: {args.ref_clips} clip(s) of the workload per step, fp32, on the "
                                          f"host CPU ({torch.get_num_threads()} threads); rank 0 only"),
-        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{args.steps} steps x {args.ref_clips} clip(s), oracle/vit_oracle.py fp32, "
-                                   f"{torch.get_num_threads()} threads"},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": os.cpu_count(), "kind": kind,
+                         "sample": f"{args.steps} steps x {args.ref_clips} clip(s), "
+                                   f"{'unmodified reference modeling_finetune.py (oracle/_ref)' if kind == 'reference' else 'oracle/vit_oracle.py'}"
+                                   f" fp32, {torch.get_num_threads()} threads"},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     out.emit(json.dumps(line))
+
+
+def extra_configs(args, dev, rank, world, synth, mf):
+    """BASELINE configs 3 and 5 as extra keys of the bench line (the headline stays config 2).
+    c3: ViT-L/16, 8 synthetic 100-frame videos = 8 x 85 windows through SlidingWindowRunner.score_videos, the window
+        index space sharded over the ranks (STRONG scaling) with one score gather; the gathered [680, 2] table is compared
+        bit for bit with the same table computed by one rank alone inside this job (rff:311-314, eff:449-454, ut:791-810).
+    c5: ViT-B graph-replay batch sweep B = 1 ... 256 clips per GPU on every rank (test_efficiency.py shape, te:174-194)."""
+    from simple_tad_b200 import efficiency
+    from simple_tad_b200.runner import SlidingWindowRunner
+    out = {}
+    # ---- config 3
+    name = "vit_large_patch16_224"
+    model = mf.__dict__[name](num_classes=2, all_frames=16, tubelet_size=2, init_scale=1.0, final_reduction="fc_norm",
+                              use_flash_attn=True)
+    model.load_state_dict(synth.make_state_dict(name, seed=3))
+    model = model.to(dev).eval()
+    videos = [synth.make_video(100, seed=300 + v).pin_memory() for v in range(8)]
+    runner = SlidingWindowRunner(model, batch_windows=64, device=dev)
+    runner.score_videos(videos[:1])  # warm-up: weight packing, workspace
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    times = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        table = runner.score_videos(videos)  # sharded + gathered; frames go host -> device inside
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    t = torch.tensor([min(times)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    c3 = {"workload": "vit_large_patch16_224, 8 videos x 100 frames = 680 windows, clip-sharded, one score gather",
+          "scaling": "strong", "n_gpus": world, "windows": int(table.shape[0]), "clips_per_s": table.shape[0] / float(t),
+          "seconds": float(t), "host_frames_in": True}
+    if world > 1:
+        # the same table by ONE rank alone (no process group involved): every rank checks its gathered copy against it
+        lengths = [int(v.shape[0]) for v in videos]
+        alone = None
+        if rank == 0:
+            t0 = time.perf_counter()
+            alone = runner._score_segments(videos, lengths, [(v, 0, lengths[v] - 15) for v in range(8)])
+            torch.cuda.synchronize()
+            c3["single_rank_seconds"] = time.perf_counter() - t0
+        else:
+            alone = torch.empty_like(table)
+        dist.broadcast(alone, src=0)
+        same = torch.tensor([int(torch.equal(alone, table))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        c3["gathered_table_bit_identical_to_single_rank"] = bool(int(same))
+        if rank == 0:
+            c3["efficiency_vs_single_rank"] = c3["single_rank_seconds"] / (world * c3["seconds"])
+    out["c3"] = c3
+    del model, runner, videos
+    torch.cuda.empty_cache()
+    # ---- config 5
+    rows = efficiency.batch_sweep("VideoMAE-B", batches=(1, 2, 4, 8, 16, 32, 64, 128, 256), warmup=10, iters=40, quiet=True)
+    out["c5"] = {"workload": "vit_base_patch16_224 CUDA-graph replay, B clips per GPU resident in HBM (fp32 in), per rank",
+                 "n_gpus": world, "rows": [{k: r[k] for k in ("batch_per_gpu", "ms_max_over_ranks", "clips_per_s")} for r in rows]}
+    return out
 
 
 class OnlyJsonOnStdout:
@@ -257,6 +336,15 @@ def main():
     for i in range(args.warmup):
         step(i)
     launches_per_step = prep.last_launches + 1  # + the fp32->bf16 cast of the frames
+    # untimed pre-heat: the part settles to its power-capped clock within ~2 s of dense tensor work; the timed region
+    # then sees the sustained clock the roofline denominator (bf16_tflops_sustained) was measured at
+    torch.cuda.synchronize()
+    t_heat, n_heat = time.perf_counter(), 0
+    while time.perf_counter() - t_heat < args.preheat_s:
+        for i in range(4):
+            step(i)
+        torch.cuda.synchronize()
+        n_heat += 4
     sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -328,6 +416,8 @@ def main():
         alg = ncu["algorithmic_bytes_per_launch"]
         roofline["traffic_detail"] = {"dram_bytes_per_launch": per, "algorithmic_bytes_per_launch": alg,
                                       "source": ncu["source"]}
+        roofline["traffic_source"] = ("NOT measured in this run (ncu cannot run inside the timed bench): read from "
+                                      "profiles/ncu_gemm_dram.json, captured " + str(ncu.get("captured", "in round 1")))
 
     # ---------------------------------------------------------------- end to end through the public runner API
     # Host frames as the reference's callers hold them after cv2.resize (uint8 HWC BGR, ri:79-81): every step copies
@@ -336,7 +426,7 @@ def main():
     gen = torch.Generator().manual_seed(77 + rank)
     host_u8 = [torch.randint(0, 256, (T_frames, 224, 224, 3), generator=gen, dtype=torch.uint8).pin_memory()
                for _ in range(n_bufs)]
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, args.steps)
     runner.score_frames_u8(host_u8[0], bgr=True)
     sync_all()
     t0 = time.perf_counter()
@@ -370,7 +460,15 @@ def main():
                 "gpu_launches_per_step": e2e_launches,
                 "api": "SlidingWindowRunner.score_frames_u8(pinned uint8 HWC BGR frames) -> host (logits, probs)"},
         "gpu_launches": launches_per_step * args.steps,
+        "preheat": {"seconds": args.preheat_s, "untimed_steps": n_heat},
+        "notes": ["`value` (frames resident in HBM as fp32) includes the fp32->bf16 cast of the step's frames "
+                  f"({T_frames * 3 * 224 * 224 * 4 / 1e6:.0f} MB read); `e2e` starts from pinned uint8 host frames (H2D copy + "
+                  "uint8 normalise kernel instead of the cast) and ends with the scores on the host: the two legs do not time "
+                  "the same work, so e2e can exceed value",
+                  "the reference arm (--impl reference) runs a bounded sample (--ref-clips clips per step) of this workload"],
     }
+    if not args.no_extras:
+        line.update(extra_configs(args, dev, rank, world, synth, mf))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.model)
     if world > 1:

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define STAD_ABI_VERSION 5
+#define STAD_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define STAD_API __attribute__((visibility("default")))
@@ -64,6 +64,12 @@ typedef struct stad_input {
   int32_t start;    /* FRAMES: first frame of clip 0 */
   int32_t stride;   /* FRAMES: frame step between consecutive clips (1 = every window, dota.py:209) */
   int32_t frame_step; /* FRAMES: frame distance inside a clip; 0 or 1 = consecutive frames */
+  const int32_t* window_starts; /* FRAMES, optional (ABI v6): DEVICE array [B] with the first frame of every clip; when
+                                   non-NULL it replaces start + b * stride.  One batch can then hold windows of several
+                                   videos laid end to end in the frame buffer (final_test over a dataset of videos,
+                                   eff:385-463: the DataLoader batches windows across video boundaries, rff:311-314).
+                                   The caller guarantees window_starts[b] + (frames - 1) * frame_step < n_frames;
+                                   frames beyond the buffer read as zeros (tensor-map bounds), never out of bounds. */
 } stad_input;
 
 /* Geometry of one model (PatchEmbed mf:172-183, VisionTransformer mf:211-234). */

@@ -29,7 +29,7 @@ PIX_TOK_STEP, PIX_VAL_STEP = 11, 6               # pretrain fixtures keep pixels
 HID_CH = [0, 1, 2, 63, 64, 191, 255, 383]         # sampled channels (valid for D >= 384)
 
 
-def install_shims():
+def install_shims(ref_path=None):
     if "timm" not in sys.modules:
         timm = types.ModuleType("timm")
         models = types.ModuleType("timm.models")
@@ -62,8 +62,9 @@ def install_shims():
         ns = types.ModuleType("natsort")
         ns.natsorted = sorted
         sys.modules["natsort"] = ns
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
+    ref_path = ref_path or REF
+    if ref_path not in sys.path:
+        sys.path.insert(0, ref_path)
 
 
 def ref_classifier(arch, sd, init_values=0.0):

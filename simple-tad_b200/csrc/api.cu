@@ -9,7 +9,7 @@ namespace stad {
 namespace {
 
 std::mutex g_init_mutex;
-bool g_inited = false;
+bool g_inited[64] = {};  // per device: cudaFuncSetAttribute (dynamic shared memory opt-in) is a per-device setting
 
 inline cudaStream_t as_stream(stad_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -48,6 +48,7 @@ int make_geom(const stad_dims* d, const stad_input* in, int B, PatchGeom* pg) {
   pg->start = in->start;
   pg->stride = in->stride;
   pg->fstep = in->frame_step > 1 ? in->frame_step : 1;
+  pg->win_start = nullptr;
   if (in->mode == STAD_IN_CLIPS) {
     pg->n_planes = B * d->in_chans * d->frames;
     pg->start = 0;
@@ -55,9 +56,17 @@ int make_geom(const stad_dims* d, const stad_input* in, int B, PatchGeom* pg) {
   } else if (in->mode == STAD_IN_FRAMES) {
     STAD_CHECK_ARG(in->stride >= 1 && in->start >= 0, "frames input: start=%d stride=%d", in->start, in->stride);
     STAD_CHECK_ARG(in->frame_step >= 0, "frames input: frame_step=%d", in->frame_step);
-    STAD_CHECK_ARG(in->start + (B - 1) * in->stride + (d->frames - 1) * pg->fstep < in->n_frames,
-                   "frames input: clip %d needs frame %d but only %d frames are resident", B - 1,
-                   in->start + (B - 1) * in->stride + (d->frames - 1) * pg->fstep, in->n_frames);
+    if (in->window_starts != nullptr) {
+      // explicit first frames (device memory: their range is the caller's contract, see stad.h)
+      STAD_CHECK_ARG((d->frames - 1) * pg->fstep < in->n_frames, "frames input: a clip spans %d frames but only %d are resident",
+                     (d->frames - 1) * pg->fstep + 1, in->n_frames);
+      if (reinterpret_cast<uintptr_t>(in->window_starts) & 3) return fail(STAD_E_ALIGN, "window_starts must be 4-byte aligned");
+      pg->win_start = in->window_starts;
+    } else {
+      STAD_CHECK_ARG(in->start + (B - 1) * in->stride + (d->frames - 1) * pg->fstep < in->n_frames,
+                     "frames input: clip %d needs frame %d but only %d frames are resident", B - 1,
+                     in->start + (B - 1) * in->stride + (d->frames - 1) * pg->fstep, in->n_frames);
+    }
     pg->n_planes = in->n_frames * d->in_chans;
   } else {
     return fail(STAD_E_SHAPE, "unknown input mode %d", in->mode);
@@ -284,11 +293,11 @@ int stad_init(int device) {
     return fail(STAD_E_ARCH, "stad_init: device %d is sm_%d%d; libstad is built for sm_100a only and has no other path",
                 device, major, minor);
   STAD_CUDA_OK(cudaSetDevice(device));
-  if (g_inited) return STAD_OK;
+  if (device < 64 && g_inited[device]) return STAD_OK;
   int rc;
   if ((rc = gemm_init())) return rc;
   if ((rc = attention_init())) return rc;
-  g_inited = true;
+  if (device < 64) g_inited[device] = true;
   return STAD_OK;
 }
 

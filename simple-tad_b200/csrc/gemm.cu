@@ -176,13 +176,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int m_tile = m_tile_of(tile);
       const int n_tile = tile % p.n_tiles;
       int a_bytes = C::A_BYTES;
-      int pe_b = 0, pe_tp = 0, pe_h0 = 0;
+      int pe_b = 0, pe_tp = 0, pe_h0 = 0, pe_f0 = 0;
       if constexpr (kPatch) {
         const PatchGeom& g = p.pg;
         const int hh = m_tile % g.h_tiles;
         pe_tp = (m_tile / g.h_tiles) % g.Tp;
         pe_b = m_tile / (g.h_tiles * g.Tp);
         pe_h0 = hh * g.hp_tile;
+        // first frame of clip pe_b in the frame buffer: an arithmetic progression, or the caller's list (ABI v6)
+        pe_f0 = g.win_start != nullptr ? __ldg(g.win_start + pe_b) : g.start + pe_b * g.stride;
         a_bytes = g.Wp * g.hp_tile * BK * 2;  // 4 full boxes, out-of-range h' rows arrive as zeros
       }
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -204,8 +206,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int dt = (kb >> 2) % g.tubelet;
             const int dh0 = (kb & 3) * 4;
             const int t = pe_tp * g.tubelet + dt;
-            const int plane = g.mode == STAD_IN_CLIPS ? (pe_b * g.C + c) * g.T + t
-                                                      : (g.start + pe_b * g.stride + t * g.fstep) * g.C + c;
+            const int plane = g.mode == STAD_IN_CLIPS ? (pe_b * g.C + c) * g.T + t : (pe_f0 + t * g.fstep) * g.C + c;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)  // K-slice k = line dh0 + k: [tokens][16 dw] at sa + k * 4 KB
               tma_load_5d(sa + k * (BM * UMMA_K * 2), &tmap_a, &full_bar[stage], 0, 0, pe_h0, dh0 + k, plane);

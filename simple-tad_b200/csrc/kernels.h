@@ -14,6 +14,7 @@ struct PatchGeom {
   int mode, start, stride;  // STAD_IN_CLIPS / STAD_IN_FRAMES
   int fstep;                // FRAMES: frame distance inside a clip (>= 1)
   int n_planes;             // extent of the plane dimension of the input tensor map
+  const int32_t* win_start; // FRAMES, optional: device array [B], first frame of clip b (replaces start + b * stride)
 };
 
 enum : int { EPI_LN = 1, EPI_GELU = 2, EPI_RESID = 4, EPI_POS = 8, EPI_STATS = 16 };

@@ -450,9 +450,12 @@ gather_patches_kernel(const bf16* __restrict__ planes, PatchGeom pg, const int32
   const int dt = (k >> 8) % pg.tubelet;
   const int c = (k >> 8) / pg.tubelet;
   const int t = tp * pg.tubelet + dt;
-  const int plane = pg.mode == STAD_IN_CLIPS ? (b * pg.C + c) * pg.T + t : (pg.start + b * pg.stride + t * pg.fstep) * pg.C + c;
+  const int f0 = pg.win_start != nullptr ? __ldg(pg.win_start + b) : pg.start + b * pg.stride;
+  const int plane = pg.mode == STAD_IN_CLIPS ? (b * pg.C + c) * pg.T + t : (f0 + t * pg.fstep) * pg.C + c;
   const size_t src = (static_cast<size_t>(plane) * pg.img_h + hp * 16 + dh) * pg.img_w + wp * 16 + dw;
-  reinterpret_cast<uint4*>(out)[i] = __ldg(reinterpret_cast<const uint4*>(planes + src));
+  // a caller-supplied first frame beyond the buffer reads as zeros, like the tensor-map path (never out of bounds)
+  reinterpret_cast<uint4*>(out)[i] = (plane >= 0 && plane < pg.n_planes) ? __ldg(reinterpret_cast<const uint4*>(planes + src))
+                                                                         : make_uint4(0u, 0u, 0u, 0u);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

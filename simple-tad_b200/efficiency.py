@@ -50,6 +50,10 @@ class GraphedForward:
     def __init__(self, model, example):
         self.model = model
         self.static_x = example.clone()
+        self._capture()
+
+    def _capture(self):
+        model = self.model
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):           # warm-up off the capture stream: weight packing, workspace allocation
@@ -60,8 +64,13 @@ class GraphedForward:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = model(self.static_x)
+        self._token = model.prepare().graph_token()
 
     def run(self, x=None):
+        # the graph has the prepared model's weight and workspace pointers baked in: re-capture when either has changed
+        # since (weights reloaded or moved; the workspace reallocated for a larger batch by another caller)
+        if self.model.prepare().graph_token() != self._token:
+            self._capture()
         if x is not None and x.data_ptr() != self.static_x.data_ptr():
             self.static_x.copy_(x, non_blocking=True)
         self.graph.replay()

@@ -350,6 +350,13 @@ class _PreparedModel:
         self._ws_key = None
         self._in_bf16 = None
 
+    def graph_token(self):
+        """What a captured CUDA graph of a forward has baked in: this prepared model (the packed weights) and the raw
+        pointers of its workspace and input-cast buffer.  A graph is only replayable while the token is unchanged
+        (another caller with a larger batch reallocates the workspace; a weight change builds a new prepared model)."""
+        return (id(self), self._workspace.data_ptr() if self._workspace is not None else 0,
+                self._in_bf16.data_ptr() if self._in_bf16 is not None else 0)
+
     def workspace(self, B, n_tok):
         need = _lib.load().stad_workspace_bytes(C.byref(self.dims), B, n_tok)
         if self._workspace is None or self._workspace.numel() < need:
@@ -555,27 +562,42 @@ class VisionTransformer(_StadBackbone):
         return prep.run(inp, B, pe.num_patches, want=want)
 
     @torch.no_grad()
-    def forward_windows(self, frames, start=0, count=None, stride=1, frame_step=1):
+    def forward_windows(self, frames, start=0, count=None, stride=1, frame_step=1, starts=None):
         """Sliding-window inference straight from a resident frame buffer (ri:69-109, dota.py:204-223):
         frames [F, C, H, W] (fp32 or bf16, already normalised); frame t of window b is frames[start + b*stride +
         t*frame_step] (frame_step = orig_fps // target_fps, dataset/sequencing.py:45-58; 1 = consecutive frames).
+        starts: optional int32 CUDA tensor [count] with the first frame of every window instead of start + b*stride —
+        one batch can then hold windows of several videos laid end to end in `frames` (final_test, eff:385-463).
         Returns (logits, probs), each [count, num_classes], without materialising the [count, C, T, H, W] clips."""
         self._check_supported()
         if frames.dim() != 4 or not frames.is_cuda:
             raise ValueError(f"expected CUDA frames [F, C, H, W], got {tuple(frames.shape)} on {frames.device}")
+        pe = self.patch_embed
+        # the tensor map is built from the MODEL's geometry: frames of another size would be read with the wrong strides
+        assert frames.shape[2] == pe.img_size[0] and frames.shape[3] == pe.img_size[1], \
+            f"Input image size ({frames.shape[2]}*{frames.shape[3]}) doesn't match model ({pe.img_size[0]}*{pe.img_size[1]})."
+        if frames.shape[1] != pe.in_chans:
+            raise ValueError(f"expected frames [F, {pe.in_chans}, H, W], got {tuple(frames.shape)}")
         F_ = frames.shape[0]
         T = self.num_frames
         if frame_step < 1 or stride < 1:
             raise ValueError(f"stride={stride} and frame_step={frame_step} must be >= 1")
         span = (T - 1) * frame_step + 1                      # frames a window covers (sequencing.py:48-50)
-        if count is None:
+        if starts is not None:
+            if starts.dim() != 1 or starts.dtype != torch.int32 or starts.device != frames.device:
+                raise ValueError("starts must be a 1-D int32 tensor on the device of the frames")
+            count = starts.numel() if count is None else count
+            if count > starts.numel():
+                raise ValueError(f"count={count} but only {starts.numel()} window starts were given")
+        elif count is None:
             count = (F_ - span - start) // stride + 1
-        if count < 1:
+        if count < 1 or F_ < span:
             raise ValueError(f"{F_} frames hold no window of {T} frames (frame step {frame_step}) from start={start}")
         prep = self.prepare(frames.device)
         fb = prep.input_bf16(frames)
-        inp = _lib.make_input(fb, _lib.STAD_IN_FRAMES, n_frames=F_, start=start, stride=stride, frame_step=frame_step)
-        res = prep.run(inp, count, self.patch_embed.num_patches, want=("logits", "probs"))
+        inp = _lib.make_input(fb, _lib.STAD_IN_FRAMES, n_frames=F_, start=start, stride=stride, frame_step=frame_step,
+                              window_starts=starts)
+        res = prep.run(inp, count, pe.num_patches, want=("logits", "probs"))
         return res["logits"], res["probs"]
 
     @torch.no_grad()

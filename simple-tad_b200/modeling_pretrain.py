@@ -36,7 +36,13 @@ def visible_token_indices(mask, n_visible=None):
         raise ValueError(f"mask must be [B, N] bool, got {tuple(mask.shape)}")
     mask = mask.bool()
     if n_visible is None:
-        n_visible = int((~mask[0]).sum())  # one host sync, as x[~mask] has in the reference
+        # one host sync, as x[~mask] has in the reference; every clip must keep the same number of tokens — the
+        # reference fails loudly otherwise (x[~mask].reshape(B, -1, C) raises, mp:98), and so does this
+        counts = (~mask).sum(1)
+        lo, hi = int(counts.min()), int(counts.max())
+        if lo != hi:
+            raise ValueError(f"mask keeps between {lo} and {hi} tokens per clip; every clip must keep the same number")
+        n_visible = lo
     # stable argsort of the mask puts the visible (False) positions first, in their original order
     order = torch.argsort(mask.to(torch.uint8), dim=1, stable=True)
     return order[:, :n_visible].to(torch.int32).contiguous(), n_visible

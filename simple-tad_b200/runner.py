@@ -96,11 +96,15 @@ class SlidingWindowRunner:
         if F_ < self.span:
             raise ValueError(f"need at least {self.span} frames, got {F_}")
         first = (F_ - self.span) % self.stride      # the last window ends on the last frame (sequencing.py:55)
+        # fp32 frames are cast to bf16 ONCE per buffer here, not once per batch of windows inside forward_windows
+        dev = self.model.prepare(dev.device).input_bf16(dev)
         logits, probs = [], []
         for w0 in range(0, n, self.batch_windows):
             cnt = min(self.batch_windows, n - w0)
             lg, pr = self.model.forward_windows(dev, start=first + w0 * self.stride, count=cnt, stride=self.stride,
                                                 frame_step=self.frame_step)
+            if n > self.batch_windows:  # the model returns views of reused output buffers
+                lg, pr = lg.clone(), pr.clone()
             logits.append(lg)
             probs.append(pr)
         return (logits[0], probs[0]) if len(logits) == 1 else (torch.cat(logits), torch.cat(probs))
@@ -139,6 +143,60 @@ class SlidingWindowRunner:
         logits, probs = self.score_frames_device(planes)
         return logits.cpu(), probs.cpu()
 
+    def plan_chunks(self, lengths, segs, max_frames=2048):
+        """Lay the frame ranges of the segments (video, first_window, n_windows) end to end in chunks of at most
+        `max_frames` frames (a segment longer than that is split by windows).  Returns a list of chunks; a chunk is a list
+        of (video, f0, f1, offset, window_starts) with [f0, f1) the source frames copied to chunk frames [offset,
+        offset + f1 - f0) and window_starts the chunk-relative first frame of every window of the piece."""
+        chunks, cur, used = [], [], 0
+        per_piece = max(1, (max_frames - self.span) // self.stride + 1)  # windows whose frames fit one chunk
+        for v, w0, cnt in segs:
+            first = (lengths[v] - self.span) % self.stride  # windows are aligned to the end of a video (sequencing.py:55)
+            done = 0
+            while done < cnt:
+                take = min(cnt - done, per_piece)
+                f0 = first + (w0 + done) * self.stride
+                f1 = first + (w0 + done + take - 1) * self.stride + self.span
+                if cur and used + (f1 - f0) > max_frames:
+                    chunks.append(cur)
+                    cur, used = [], 0
+                cur.append((v, f0, f1, used, [used + i * self.stride for i in range(take)]))
+                used += f1 - f0
+                done += take
+        if cur:
+            chunks.append(cur)
+        return chunks
+
+    @torch.no_grad()
+    def _score_segments(self, videos, lengths, segs, max_frames=2048):
+        """Logits [sum of n_windows, C] (device) of the segments, in order.  The frames of a chunk of segments are
+        uploaded once into one device buffer and every batch holds `batch_windows` windows regardless of where the
+        video boundaries fall (explicit window starts, stad_input.window_starts): a rank's shard runs FULL batches, as
+        the reference's DataLoader batches windows across videos (rff:311-314, eff:418-431)."""
+        C = self.model.num_classes
+        outs = []
+        prep = None
+        for chunk in self.plan_chunks(lengths, segs, max_frames):
+            n_frames = chunk[-1][3] + chunk[-1][2] - chunk[-1][1]
+            sample = videos[chunk[0][0]]
+            shape = (n_frames,) + tuple(sample.shape[1:])
+            numel = n_frames * sample[0].numel()
+            if self._dev_frames is None or self._dev_frames.numel() < numel or self._dev_frames.dtype != sample.dtype:
+                self._dev_frames = torch.empty(numel, dtype=sample.dtype, device=self.device)
+            buf = self._dev_frames[:numel].view(shape)
+            starts = []
+            for v, f0, f1, off, ws in chunk:
+                buf[off:off + f1 - f0].copy_(videos[v][f0:f1], non_blocking=True)
+                starts.extend(ws)
+            starts = torch.tensor(starts, dtype=torch.int32).to(self.device, non_blocking=True)
+            prep = prep or self.model.prepare(self.device)
+            planes = prep.input_bf16(buf)
+            for i in range(0, starts.numel(), self.batch_windows):
+                st = starts[i:i + self.batch_windows]
+                lg, _ = self.model.forward_windows(planes, starts=st, frame_step=self.frame_step)
+                outs.append(lg.clone())
+        return torch.cat(outs) if outs else torch.zeros(0, C, dtype=torch.float32, device=self.device)
+
     @torch.no_grad()
     def score_videos(self, videos, group=None):
         """videos: list of host frame tensors [T_v, C, H, W].  The global window index space is split into contiguous
@@ -150,15 +208,7 @@ class SlidingWindowRunner:
         _, n_total = window_segments(lengths, 0, 0, self.T, self.stride, self.frame_step)
         lo, hi, per = shard_range(n_total, world, rank)
         segs, _ = window_segments(lengths, lo, hi, self.T, self.stride, self.frame_step)
-        outs = []
-        for v, w0, cnt in segs:
-            first = (lengths[v] - self.span) % self.stride
-            f0 = first + w0 * self.stride
-            f1 = first + (w0 + cnt - 1) * self.stride + self.span
-            lg, _ = self.score_frames_device(videos[v][f0:f1])
-            outs.append(lg.clone())
-        C = self.model.num_classes
-        local = torch.cat(outs) if outs else torch.zeros(0, C, dtype=torch.float32, device=self.device)
+        local = self._score_segments(videos, lengths, segs)
         return gather_scores(local, n_total, group)
 
     @torch.no_grad()
@@ -175,22 +225,13 @@ class SlidingWindowRunner:
         _, n_total = window_segments(lengths, 0, 0, self.T, self.stride, self.frame_step)
         lo, hi, per = shard_range(n_total, world, rank)
         segs, _ = window_segments(lengths, lo, hi, self.T, self.stride, self.frame_step)
-        outs, labs = [], []
+        local = self._score_segments(videos, lengths, segs)
+        labs = []
         for v, w0, cnt in segs:
             first = (lengths[v] - self.span) % self.stride
-            f0 = first + w0 * self.stride
-            f1 = first + (w0 + cnt - 1) * self.stride + self.span
-            lg, _ = self.score_frames_device(videos[v][f0:f1])
-            outs.append(lg.clone())
             last = first + torch.arange(w0, w0 + cnt) * self.stride + self.span - 1
             labs.append(torch.as_tensor(frame_labels[v])[last].to(torch.int32))
-        C = self.model.num_classes
-        if outs:
-            local = torch.cat(outs)
-            local_labels = torch.cat(labs).to(self.device)
-        else:  # more ranks than windows: an empty shard still takes part in the reductions
-            local = torch.zeros(0, C, dtype=torch.float32, device=self.device)
-            local_labels = torch.zeros(0, dtype=torch.int32, device=self.device)
+        local_labels = (torch.cat(labs) if labs else torch.zeros(0, dtype=torch.int32)).to(self.device)
         res = M.evaluate(local.softmax(-1), local_labels, group=group)
         return res, gather_scores(local, n_total, group)
 
@@ -220,6 +261,8 @@ class StreamingScorer:
         self.n = 0
         self.use_graphs = bool(use_graphs)
         self._graphs = {}
+        self._graph_token = None
+        self._copied = None  # event: the H2D copy out of the pinned staging frame has finished
 
     def reset(self):
         self.n = 0
@@ -241,8 +284,13 @@ class StreamingScorer:
         elif frame_u8.is_cuda:
             self._stage[0].copy_(frame_u8)
         else:
+            if self._copied is not None:
+                self._copied.synchronize()  # the previous frame's asynchronous copy still reads the pinned buffer
             self._pin[0].copy_(frame_u8)
             self._stage.copy_(self._pin, non_blocking=True)
+            if self._copied is None:
+                self._copied = torch.cuda.Event()
+            self._copied.record(torch.cuda.current_stream(self.device))
         p = self.n % self.T
         for slot in (p, p + self.T):
             _lib.normalize_frames_u8(self._stage, self.mean, self.std, bgr=self.bgr, out=self.frames[slot:slot + 1])
@@ -253,6 +301,11 @@ class StreamingScorer:
         if not self.use_graphs:
             logits, probs = self._forward(start)
             return logits[0].cpu(), probs[0].cpu()
+        # a captured graph has the prepared model's weights and workspace pointers baked in: drop the graphs when either
+        # has changed since they were captured (weights reloaded / moved, workspace reallocated by a larger batch elsewhere)
+        token = self.model.prepare(self.device).graph_token()
+        if token != self._graph_token:
+            self._graphs.clear()
         g = self._graphs.get(start)
         if g is None:
             side = torch.cuda.Stream(device=self.device)
@@ -263,6 +316,10 @@ class StreamingScorer:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 out = self._forward(start)
+            new_token = self.model.prepare(self.device).graph_token()
+            if new_token != self._graph_token:  # (first capture, or the warm-up above moved the workspace)
+                self._graphs.clear()
+                self._graph_token = new_token
             g = self._graphs[start] = (graph, out)
         g[0].replay()
         return g[1][0][0].cpu(), g[1][1][0].cpu()

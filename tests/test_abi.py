@@ -41,9 +41,9 @@ def test_abi_version_and_error_string(lib):
 
 
 def test_struct_layouts_match_header(lib):
-    # stad_input: pointer + 5 x int32 (+ 4 bytes of tail padding); stad_dims: 11 x int32; stad_block: 10 pointers;
-    # stad_outputs: 4 pointers
-    assert ctypes.sizeof(lib.StadInput) == 32
+    # stad_input: pointer + 5 x int32 (+ 4 bytes of padding) + pointer (ABI v6: window_starts); stad_dims: 11 x int32;
+    # stad_block: 10 pointers; stad_outputs: 4 pointers
+    assert ctypes.sizeof(lib.StadInput) == 40
     assert ctypes.sizeof(lib.StadDims) == 44
     assert ctypes.sizeof(lib.StadBlock) == 80
     assert ctypes.sizeof(lib.StadOutputs) == 32

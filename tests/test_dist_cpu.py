@@ -118,10 +118,17 @@ class _IndexModel(torch.nn.Module):
         self.p = torch.nn.Parameter(torch.zeros(1))
         self.num_frames, self.num_classes = frames_per_clip, 2
 
-    def forward_windows(self, frames, start=0, count=None, stride=1, frame_step=1):
-        last = start + torch.arange(count) * stride + (self.num_frames - 1) * frame_step
-        first = start + torch.arange(count) * stride
-        # frame i of video v holds 1000 * v + i in every element
+    def prepare(self, device=None):
+        class _Prepared:  # the real model casts fp32 frames to bf16 once per buffer here; the stand-in keeps them
+            def input_bf16(self, x):
+                return x
+        return _Prepared()
+
+    def forward_windows(self, frames, start=0, count=None, stride=1, frame_step=1, starts=None):
+        first = starts.long() if starts is not None else start + torch.arange(count) * stride
+        last = first + (self.num_frames - 1) * frame_step
+        self.batches = getattr(self, "batches", []) + [int(first.numel())]
+        # frame i of video v holds 1000 * v + i in every element: a window that straddled two videos would fail here
         assert torch.equal(frames[first, 0, 0, 0] + (self.num_frames - 1) * frame_step, frames[last, 0, 0, 0])
         lg = torch.stack([frames[last, 0, 0, 0], frames[first, 0, 0, 0]], 1).float()
         return lg, lg.softmax(-1)
@@ -164,3 +171,38 @@ def test_score_videos_windows_follow_the_sequencer_world_size_2_gloo(tmp_path, s
     for r in range(world):
         got = torch.load(os.path.join(str(tmp_path), f"s{r}.pt"))
         assert got.shape == want.shape and torch.equal(got, want), f"rank {r}: window table differs from the sequencer's"
+
+
+def test_score_videos_runs_full_batches_across_video_boundaries():
+    """BASELINE config 3 shape (8 videos x 100 frames = 8 x 85 windows): the shard of a rank is scored in FULL batches of
+    `batch_windows` windows wherever the video boundaries fall (the reference's DataLoader batches windows across
+    videos, rff:311-314), in chunks of at most `max_frames` resident frames; the table is the sequencer's."""
+    from simple_tad_b200.runner import SlidingWindowRunner
+    lengths = [100] * 8
+    model = _IndexModel()
+    runner = SlidingWindowRunner(model, batch_windows=64, device="cpu")
+    full = runner.score_videos(_videos(lengths))
+    assert model.batches == [64] * 10 + [40]
+    want = torch.tensor([(1000.0 * v + w + 15, 1000.0 * v + w) for v in range(8) for w in range(85)])
+    assert torch.equal(full, want)
+    # chunking by resident frames: pieces never exceed the budget, a long video is split by windows, nothing is lost
+    runner = SlidingWindowRunner(_IndexModel(), batch_windows=16, device="cpu", stride=2)
+    lengths = [300, 16, 40, 17]
+    segs = [(0, 0, 143), (1, 0, 1), (2, 0, 13), (3, 0, 1)]
+    chunks = runner.plan_chunks(lengths, segs, max_frames=64)
+    n_windows = 0
+    for chunk in chunks:
+        used = 0
+        for v, f0, f1, off, ws in chunk:
+            assert off == used and 0 <= f0 < f1 <= lengths[v]
+            assert all(off <= w and w + 16 <= off + (f1 - f0) for w in ws)
+            used += f1 - f0
+            n_windows += len(ws)
+        assert used <= 64
+    assert n_windows == sum(c for _, _, c in segs)
+    got = runner._score_segments(_videos(lengths), lengths, segs, max_frames=64)
+    want = []
+    for v, T in enumerate(lengths):
+        first = (T - 16) % 2
+        want += [(1000.0 * v + first + 2 * w + 15, 1000.0 * v + first + 2 * w) for w in range((T - 16) // 2 + 1)]
+    assert torch.equal(got, torch.tensor(want))

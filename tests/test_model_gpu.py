@@ -340,6 +340,25 @@ def test_runner_evaluate_videos_matches_metrics_on_the_gathered_scores():
     np.testing.assert_allclose(res["thresholded"]["mcc"], th["mcc"], atol=1e-12)
 
 
+def test_score_videos_batches_across_video_boundaries_bit_identical():
+    """stad_input.window_starts (ABI v6): windows of several videos laid end to end in one frame buffer and scored in
+    full batches give bit-for-bit the scores of every video scored on its own (same kernels, same per-clip arithmetic)."""
+    from simple_tad_b200.runner import SlidingWindowRunner
+    sd = synth.make_state_dict("vit_small_d2", seed=11)
+    model = parity.build_classifier("vit_small_d2", sd)
+    videos = [synth.make_video(T, seed=60 + i) for i, T in enumerate((21, 16, 27, 19))]
+    runner = SlidingWindowRunner(model, batch_windows=8)
+    together = runner.score_videos(videos)                       # 6 + 1 + 12 + 4 = 23 windows: batches 8, 8, 7
+    alone = torch.cat([runner.score_frames_device(v)[0].clone() for v in videos])
+    assert together.shape == (23, 2) and torch.equal(together, alone)
+    # a chunk budget smaller than a video splits it by windows without changing a bit
+    small = runner._score_segments(videos, [int(v.shape[0]) for v in videos], [(i, 0, int(v.shape[0]) - 15) for i, v in enumerate(videos)],
+                                   max_frames=20)
+    assert torch.equal(small, alone)
+    with pytest.raises(AssertionError):                            # frames of another size: the reference's PatchEmbed assert
+        model.forward_windows(torch.zeros(20, 3, 112, 112, device=DEV))
+
+
 def test_streaming_scorer_matches_the_sliding_windows():
     """run_inference.py:69-109 shape: frames arrive one by one; from the 16th on every push returns the score of the
     window ending at that frame, equal to forward_windows over the whole video (same kernels; the batch size changes
@@ -437,3 +456,49 @@ def test_errors_follow_reference_conventions():
         _lib.gemm_bias_residual(torch.zeros(128, 72, device=DEV, dtype=torch.bfloat16),
                                 torch.zeros(64, 72, device=DEV, dtype=torch.bfloat16))
     assert "K=72" in _lib.last_error()
+
+
+def _nccl_worker(rank, world, port, tmp):
+    import os
+    import sys
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from simple_tad_b200.runner import SlidingWindowRunner
+    sd = synth.make_state_dict("vit_small_d2", seed=11)
+    model = parity.build_classifier("vit_small_d2", sd, device=f"cuda:{rank}")
+    videos = [synth.make_video(T, seed=70 + i) for i, T in enumerate((40, 16, 33, 25))]
+    gen = torch.Generator().manual_seed(2)
+    labels = [(torch.rand(v.shape[0], generator=gen) < 0.4).long() for v in videos]
+    runner = SlidingWindowRunner(model, batch_windows=8)
+    table = runner.score_videos(videos)                   # sharded over the ranks, ONE NCCL all-gather
+    res, table2 = runner.evaluate_videos(videos, labels)  # + the all-reduce of the metric count table
+    torch.save((table.cpu(), table2.cpu(), res["counts"]), os.path.join(tmp, f"nccl{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL over NVLink)")
+def test_score_videos_two_ranks_nccl_matches_one_rank(tmp_path):
+    """final_test + gather_predictions (eff:385-463, ut:791-810) on two B200s: the clip-sharded, NCCL-gathered score
+    table is bit-identical on both ranks and to the table one rank computes alone; so are the all-reduced metric counts."""
+    import socket
+    import torch.multiprocessing as mp
+    from simple_tad_b200.runner import SlidingWindowRunner
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    sd = synth.make_state_dict("vit_small_d2", seed=11)
+    model = parity.build_classifier("vit_small_d2", sd)
+    videos = [synth.make_video(T, seed=70 + i) for i, T in enumerate((40, 16, 33, 25))]
+    gen = torch.Generator().manual_seed(2)
+    labels = [(torch.rand(v.shape[0], generator=gen) < 0.4).long() for v in videos]
+    runner = SlidingWindowRunner(model, batch_windows=8)
+    res, alone = runner.evaluate_videos(videos, labels)
+    for r in range(2):
+        t1, t2, counts = torch.load(str(tmp_path / f"nccl{r}.pt"), weights_only=False)
+        assert torch.equal(t1, alone.cpu()) and torch.equal(t2, alone.cpu())
+        for k in ("tp", "fp", "tn", "fn"):
+            assert (counts[k] == res["counts"][k]).all()
