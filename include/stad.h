@@ -64,6 +64,12 @@ typedef struct stad_input {
   int32_t start;    /* FRAMES: first frame of clip 0 */
   int32_t stride;   /* FRAMES: frame step between consecutive clips (1 = every window, dota.py:209) */
   int32_t frame_step; /* FRAMES: frame distance inside a clip; 0 or 1 = consecutive frames */
+  int32_t tubelet_reuse; /* FRAMES (ABI v6): non-zero lets stad_vit_forward embed every DISTINCT tubelet of the batch once
+                            and assemble the windows from them (consecutive stride-1 windows share 7 of their 8 tubelets
+                            with the window two frames on, ri:97-101).  Used when tubelet * frame_step is a multiple of
+                            stride and at least a quarter of the embeddings is shared; the tubelet embedding is then
+                            rounded to bf16 before the position table is added (one extra rounding, within the path's
+                            tolerance; 0 keeps the frames path bit-identical to the clips path) */
   const int32_t* window_starts; /* FRAMES, optional (ABI v6): DEVICE array [B] with the first frame of every clip; when
                                    non-NULL it replaces start + b * stride.  One batch can then hold windows of several
                                    videos laid end to end in the frame buffer (final_test over a dataset of videos,

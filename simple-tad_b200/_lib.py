@@ -26,7 +26,8 @@ EXPORTS = (
 
 class StadInput(C.Structure):
     _fields_ = [("data", C.c_void_p), ("mode", C.c_int32), ("n_frames", C.c_int32), ("start", C.c_int32),
-                ("stride", C.c_int32), ("frame_step", C.c_int32), ("window_starts", C.c_void_p)]
+                ("stride", C.c_int32), ("frame_step", C.c_int32), ("tubelet_reuse", C.c_int32),
+                ("window_starts", C.c_void_p)]
 
 
 class StadDims(C.Structure):
@@ -325,14 +326,15 @@ def make_dims(img_h=224, img_w=224, patch=16, tubelet=2, frames=16, in_chans=3, 
     return StadDims(img_h, img_w, patch, tubelet, frames, in_chans, dim, depth, heads, hidden, num_classes)
 
 
-def make_input(data, mode=STAD_IN_CLIPS, n_frames=0, start=0, stride=1, frame_step=1, window_starts=None):
+def make_input(data, mode=STAD_IN_CLIPS, n_frames=0, start=0, stride=1, frame_step=1, window_starts=None,
+               tubelet_reuse=False):
     """window_starts: optional int32 CUDA tensor [B] with the first frame of every clip (ABI v6); the caller keeps it
     alive until the launch that reads it has run."""
     ws = None
     if window_starts is not None:
         _req(window_starts, torch.int32, "window_starts")
         ws = window_starts.data_ptr()
-    return StadInput(data.data_ptr(), mode, n_frames, start, stride, frame_step, ws)
+    return StadInput(data.data_ptr(), mode, n_frames, start, stride, frame_step, int(bool(tubelet_reuse)), ws)
 
 
 def patch_embed(x, w, pos_bias, dims, B, n_tok, tok_idx=None, mode=STAD_IN_CLIPS, n_frames=0, start=0, stride=1,

@@ -454,7 +454,35 @@ int stad_vit_forward(const stad_model* m, const stad_input* in, const int32_t* t
   // PatchEmbed + position table (mf:309-313 / mp:93-98).  Its epilogue also emits the LayerNorm partial sums of the
   // rows it stores, as does every GEMM below that writes the residual stream: no separate statistics pass.
   int parts = 0;
-  if (!with_cls) {
+  // Tubelet-embedding reuse across overlapping windows (ri:97-101): window b, slot t' holds the tubelet
+  // that starts at frame start + b * stride + t' * tubelet * frame_step.  When tubelet * frame_step is a multiple of the
+  // window stride these first frames form ONE arithmetic progression start + u * stride, u = b + t' * step, so the
+  // batch has n_u = (B - 1) + (Tp - 1) * step + 1 distinct tubelets instead of B * Tp (stride-1 windows of a 16-frame,
+  // tubelet-2 model: 64 + 14 instead of 512).  Each is embedded once (the patch GEMM over n_u one-tubelet "clips", no
+  // position table, into the not-yet-used hidden buffer) and one row kernel lays out the windows, adds the position
+  // table and writes the LayerNorm statistics of norm1 of the first block.
+  int reuse_step = -1, n_u = 0;
+  const int Tp = d->frames / d->tubelet;
+  if (!with_cls && tok_idx == nullptr && in != nullptr && in->mode == STAD_IN_FRAMES && in->tubelet_reuse &&
+      in->window_starts == nullptr && in->stride >= 1 && n_tok == full_tokens(d)) {
+    const int tf = d->tubelet * (in->frame_step > 1 ? in->frame_step : 1);
+    if (tf % in->stride == 0) {
+      const int step = tf / in->stride;
+      n_u = (B - 1) + (Tp - 1) * step + 1;
+      if (4ll * n_u <= 3ll * B * Tp) reuse_step = step;  // at least a quarter of the embeddings is shared
+    }
+  }
+  if (reuse_step >= 0) {
+    stad_dims d1 = *d;
+    d1.frames = d->tubelet;  // a "clip" of one tubelet: Tp = 1
+    if ((rc = patch_embed_impl(in, m->w_patch, /*pos_bias=*/nullptr, nullptr, ws.hidden, nullptr, &d1, n_u, full_tokens(&d1),
+                               stream, &launches)))
+      return rc;
+    const int HW = (d->img_h / 16) * (d->img_w / 16);
+    if ((rc = launch_window_assemble(ws.hidden, m->pos_bias, ws.x, ws.stats, B, Tp, HW, D, reuse_step, m->eps, stream)))
+      return rc;
+    launches += 1;
+  } else if (!with_cls) {
     if ((rc = patch_embed_impl(in, m->w_patch, m->pos_bias, tok_idx, ws.x, ws.gather, d, B, n_tok, stream, &launches,
                                ws.parts, &parts)))
       return rc;

@@ -372,7 +372,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       float st_sum = 0.f, st_sq = 0.f;  // EPI_STATS: running (sum, sumsq) of this thread's part of the row
       const float* pos_row = nullptr;
       if constexpr (EPI & EPI_POS) {
-        if (row_ok) {
+        if (row_ok && p.pos != nullptr) {  // no table: the accumulator is stored as it is (tubelet embeddings, api.cu)
           const int pr = p.tok_idx ? __ldg(&p.tok_idx[row]) : row % p.pos_rows;
           pos_row = p.pos + static_cast<size_t>(pr) * p.N;
         }
@@ -428,7 +428,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1], f[j], f[j + 1]);
         }
         if constexpr (EPI & EPI_POS) {
-          if (row_ok) {
+          if (pos_row != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 pv = __ldg(reinterpret_cast<const float4*>(pos_row + n0 + j));
@@ -739,7 +739,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     STAD_CHECK_ARG((g.stats || (g.stat_parts && g.n_stat_parts >= 1 && g.n_stat_parts <= kMaxStatParts)) && g.colsum,
                    "gemm: LN epilogue needs stats (or partial sums) and colsum");
   if (g.epi & EPI_RESID) STAD_CHECK_ARG(g.residual, "gemm: residual epilogue needs a residual");
-  if (g.epi & EPI_POS) STAD_CHECK_ARG(g.pos && (g.tok_idx || g.pos_rows > 0), "gemm: pos epilogue needs a table");
+  if (g.epi & EPI_POS) STAD_CHECK_ARG(g.pos == nullptr || g.tok_idx || g.pos_rows > 0, "gemm: pos epilogue needs pos_rows");
   if (g.epi & EPI_STATS) STAD_CHECK_ARG(g.stats_out, "gemm: statistics epilogue needs an output buffer");
   if ((reinterpret_cast<uintptr_t>(g.stats) | reinterpret_cast<uintptr_t>(g.stats_out)) & 7)
     return fail(STAD_E_ALIGN, "gemm: statistics buffers must be 8-byte aligned");

@@ -71,6 +71,11 @@ int launch_prepend_cls(const bf16* emb, const float* cls_token, bf16* x, float2*
 int launch_gather_patches(const bf16* planes, const PatchGeom& pg, const int32_t* tok_idx, bf16* out, int B,
                           int n_tok, cudaStream_t stream);
 
+// tubelet-embedding reuse: residual stream of B overlapping windows from the embeddings of their distinct tubelets
+// (window b, slot t' uses tubelet b + t' * step) + position table + LayerNorm statistics of every row
+int launch_window_assemble(const bf16* emb, const float* pos_bias, bf16* x, float2* stats, int B, int Tp, int HW, int D,
+                           int step, float eps, cudaStream_t stream);
+
 // MAE decoder glue (modeling_pretrain.py:283-288, :174) and uint8 frame preparation (run_inference.py:15-34)
 int launch_decoder_assemble(const bf16* vis, const float* pos, const float* mask_token, const int32_t* mask_idx, bf16* x,
                             float2* stats, int B, int N, int n_vis, int D, float eps, cudaStream_t stream);

@@ -522,6 +522,67 @@ decoder_assemble_kernel(const bf16* __restrict__ vis, const float* __restrict__ 
   if (lane == 0) stats[row] = make_float2(mean, rsqrtf(var + eps));
 }
 
+// Tubelet-embedding reuse across overlapping sliding windows (run_inference.py:97-101 shifts the window by one frame:
+// 15 of its 16 frames, i.e. 7 of the 8 tubelets of every second window, are shared).  The tubelet embeddings E[u] =
+// Conv3d(frames of tubelet u) (no bias, no position) are computed ONCE per distinct tubelet by the patch-embed GEMM;
+// this kernel lays out the residual stream of every window from them:
+//   x[b, t' * HW + hw, :] = bf16(E[(b + t' * step) * HW + hw, :] + pos_bias[t' * HW + hw, :])      (mf:309-313)
+// and, in the same pass, the LayerNorm statistics (mean, rstd) of every row for norm1 of the first block.
+// One warp per output row.  Bytes: 2 B N D written (+ 8 B N); E (2 n_u HW D) and pos_bias (4 N D) are re-read from L2.
+template <int kChunks>
+__global__ void __launch_bounds__(256)
+window_assemble_kernel(const bf16* __restrict__ emb, const float* __restrict__ pos_bias, bf16* __restrict__ x,
+                       float2* __restrict__ stats, int B, int Tp, int HW, int D, int step, float eps) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int N = Tp * HW;
+  if (row >= B * N) return;
+  const int b = row / N;
+  const int tok = row - b * N;
+  const int tp = tok / HW;
+  const int hw = tok - tp * HW;
+  const int chunks = D >> 3;
+  const uint4* er = reinterpret_cast<const uint4*>(emb + (static_cast<size_t>(b + tp * step) * HW + hw) * D);
+  const float* pr = pos_bias + static_cast<size_t>(tok) * D;
+  uint4* xr = reinterpret_cast<uint4*>(x + static_cast<size_t>(row) * D);
+  float v[kChunks][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    const int idx = c * 32 + lane;
+    if (idx < chunks) {
+      float e[8];
+      unpack8(__ldg(er + idx), e);
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pr + idx * 8));
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pr + idx * 8 + 4));
+      uint4 u;
+      u.x = pack_bf16(e[0] + p0.x, e[1] + p0.y);
+      u.y = pack_bf16(e[2] + p0.z, e[3] + p0.w);
+      u.z = pack_bf16(e[4] + p1.x, e[5] + p1.y);
+      u.w = pack_bf16(e[6] + p1.z, e[7] + p1.w);
+      xr[idx] = u;
+      unpack8(u, v[c]);  // statistics of the values as stored (bf16)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[c][j];
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    const int idx = c * 32 + lane;
+    if (idx < chunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dlt = v[c][j] - mean;
+        q = fmaf(dlt, dlt, q);
+      }
+    }
+  }
+  const float var = warp_sum(q) / static_cast<float>(D);
+  if (lane == 0) stats[row] = make_float2(mean, rsqrtf(var + eps));
+}
+
 // Last n_keep rows of every clip of x[B, N, C] bf16 -> y[B, n_keep, C] fp32 (the decoder returns only the predictions
 // of the masked tokens, modeling_pretrain.py:174).  Bytes: 2 B n_keep C read + 4 B n_keep C written.
 __global__ void __launch_bounds__(256)
@@ -791,6 +852,21 @@ int launch_gather_patches(const bf16* planes, const PatchGeom& pg, const int32_t
   gather_patches_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, stream>>>(
       planes, pg, tok_idx, out, B, n_tok, K);
   STAD_LAUNCH_OK("gather_patches");
+  return STAD_OK;
+}
+
+int launch_window_assemble(const bf16* emb, const float* pos_bias, bf16* x, float2* stats, int B, int Tp, int HW, int D,
+                           int step, float eps, cudaStream_t stream) {
+  int rc = check_row_args(x, B * Tp * HW, D);
+  if (rc) return rc;
+  STAD_CHECK_ARG(step >= 0 && Tp >= 1 && HW >= 1, "window_assemble: Tp=%d HW=%d step=%d", Tp, HW, step);
+  if ((reinterpret_cast<uintptr_t>(emb) | reinterpret_cast<uintptr_t>(pos_bias)) & 15)
+    return fail(STAD_E_ALIGN, "window_assemble: emb, pos_bias must be 16-byte aligned");
+  const int rows_per_block = 8;
+  ProfScope prof(STAD_K_ASSEMBLE, 2, B * Tp * HW, D, step, stream);
+  STAD_DISPATCH_CHUNKS(D, (window_assemble_kernel<kC><<<ceil_div(B * Tp * HW, rows_per_block), rows_per_block * 32, 0, stream>>>(
+                              emb, pos_bias, x, stats, B, Tp, HW, D, step, eps)));
+  STAD_LAUNCH_OK("window_assemble");
   return STAD_OK;
 }
 

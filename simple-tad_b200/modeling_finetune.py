@@ -91,19 +91,30 @@ class Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden_features, out_features)
         self.drop = nn.Dropout(drop)
 
+    @torch.no_grad()
+    def _pack(self, device):
+        f32 = dict(dtype=torch.float32, device=device)
+        return dict(w1=self.fc1.weight.detach().to(device=device, dtype=torch.bfloat16).contiguous(),
+                    b1=self.fc1.bias.detach().to(**f32).contiguous(),
+                    zeros=torch.zeros(self.fc1.out_features, **f32),
+                    w2=self.fc2.weight.detach().to(device=device, dtype=torch.bfloat16).contiguous(),
+                    b2=self.fc2.bias.detach().to(**f32).contiguous(), ident={})
+
     def forward(self, x):
         _inference_only(self)
         B, N, _ = x.shape
         a = _as_bf16_2d(x)
         M = a.shape[0]
+        pk = _cached_pack(self, a.device, self._pack)
         # identity LayerNorm statistics (mean 0, rstd 1) turn the LN-fold epilogue into plain bias + GELU
-        ident = torch.zeros(M, 2, dtype=torch.float32, device=a.device)
-        ident[:, 1] = 1.0
-        zeros = torch.zeros(self.fc1.out_features, dtype=torch.float32, device=a.device)
-        h = _lib.ln_gemm(a, ident, self.fc1.weight.detach().to(torch.bfloat16).contiguous(),
-                         self.fc1.bias.detach().float().contiguous(), zeros, gelu=True)
-        y = _lib.gemm_bias_residual(h, self.fc2.weight.detach().to(torch.bfloat16).contiguous(),
-                                    self.fc2.bias.detach().float().contiguous())
+        ident = pk["ident"].get(M)
+        if ident is None:
+            ident = torch.zeros(M, 2, dtype=torch.float32, device=a.device)
+            ident[:, 1] = 1.0
+            pk["ident"].clear()
+            pk["ident"][M] = ident
+        h = _lib.ln_gemm(a, ident, pk["w1"], pk["b1"], pk["zeros"], gelu=True)
+        y = _lib.gemm_bias_residual(h, pk["w2"], pk["b2"])
         return y.view(B, N, -1).to(x.dtype)
 
 
@@ -149,17 +160,23 @@ class Attention(nn.Module):
             return None
         return torch.cat((self.q_bias.detach(), torch.zeros_like(self.v_bias), self.v_bias.detach())).float()
 
+    @torch.no_grad()
+    def _pack(self, device):
+        bias = self.packed_qkv_bias()
+        return dict(w_qkv=self.qkv.weight.detach().to(device=device, dtype=torch.bfloat16).contiguous(),
+                    b_qkv=None if bias is None else bias.to(device).contiguous(),
+                    w_proj=self.proj.weight.detach().to(device=device, dtype=torch.bfloat16).contiguous(),
+                    b_proj=self.proj.bias.detach().to(device=device, dtype=torch.float32).contiguous())
+
     def forward(self, x):
         _inference_only(self)
         self._check_head_dim()
         B, N, _ = x.shape
         a = _as_bf16_2d(x)
-        bias = self.packed_qkv_bias()
-        qkv = _lib.gemm_bias_residual(a, self.qkv.weight.detach().to(torch.bfloat16).contiguous(),
-                                      None if bias is None else bias.contiguous())
+        pk = _cached_pack(self, a.device, self._pack)
+        qkv = _lib.gemm_bias_residual(a, pk["w_qkv"], pk["b_qkv"])
         ctx = _lib.attention(qkv.view(B, N, 3, self.num_heads, 64), scale=self.scale)
-        y = _lib.gemm_bias_residual(ctx.view(B * N, -1), self.proj.weight.detach().to(torch.bfloat16).contiguous(),
-                                    self.proj.bias.detach().float().contiguous())
+        y = _lib.gemm_bias_residual(ctx.view(B * N, -1), pk["w_proj"], pk["b_proj"])
         return y.view(B, N, -1).to(x.dtype)
 
 
@@ -225,7 +242,7 @@ class Block(nn.Module):
         self.attn._check_head_dim()
         B, N, D = x.shape
         h = _as_bf16_2d(x)
-        pk = self.packed(h.device)
+        pk = _cached_pack(self, h.device, self.packed)
         eps1, eps2 = self.norm1.eps, self.norm2.eps
         st = _lib.row_stats(h, eps1)
         qkv = _lib.ln_gemm(h, st, pk["w_qkv"], pk["b_qkv"], pk["cs_qkv"])
@@ -274,9 +291,13 @@ class PatchEmbed(nn.Module):
         xb = x.contiguous()
         xb = _lib.cast_f32_bf16(xb) if xb.dtype == torch.float32 else xb.to(torch.bfloat16)
         D = self.embed_dim
-        w = self.proj.weight.detach().reshape(D, -1).to(torch.bfloat16).contiguous()
-        bias = self.proj.bias.detach().float() if self.proj.bias is not None else torch.zeros(D, device=x.device)
-        pos_bias = bias[None, :].expand(self.num_patches, D).contiguous()  # no position table at module level
+
+        def pack(device):
+            w = self.proj.weight.detach().reshape(D, -1).to(device=device, dtype=torch.bfloat16).contiguous()
+            bias = (self.proj.bias.detach().to(device=device, dtype=torch.float32) if self.proj.bias is not None
+                    else torch.zeros(D, device=device))
+            return w, bias[None, :].expand(self.num_patches, D).contiguous()  # no position table at module level
+        w, pos_bias = _cached_pack(self, x.device, pack)
         out = _lib.patch_embed(xb, w, pos_bias, self.stad_dims(), B, self.num_patches)
         return out.view(B, self.num_patches, D).to(x.dtype)
 
@@ -394,9 +415,40 @@ class _PreparedModel:
         return res
 
 
+# Walking module.parameters() costs ~0.4 ms for a ViT-B (162 tensors behind a de-duplicating generator) — half a
+# batch-1 forward.  The tensor LIST is therefore cached per module and rebuilt only when some module somewhere registered
+# a parameter, buffer or sub-module since (global registration hooks bump an epoch); the signature itself — (data_ptr,
+# version) of every tensor, which moves on load_state_dict / in-place updates / .to() — is re-read every time (~40 us).
+_STRUCT_EPOCH = [0]
+
+
+def _bump_struct_epoch(*args, **kwargs):
+    _STRUCT_EPOCH[0] += 1
+
+
+torch.nn.modules.module.register_module_parameter_registration_hook(_bump_struct_epoch)
+torch.nn.modules.module.register_module_buffer_registration_hook(_bump_struct_epoch)
+torch.nn.modules.module.register_module_module_registration_hook(_bump_struct_epoch)
+
+
 def _weights_signature(module):
-    return tuple((p.data_ptr(), p._version, p.device) for p in module.parameters()) + \
-        tuple((b.data_ptr(), b._version) for b in module.buffers())
+    cache = module.__dict__.get("_stad_tensor_list")
+    if cache is None or cache[0] != _STRUCT_EPOCH[0]:
+        cache = (_STRUCT_EPOCH[0], list(module.parameters()) + list(module.buffers()))
+        object.__setattr__(module, "_stad_tensor_list", cache)
+    return tuple((t.data_ptr(), t._version) for t in cache[1])
+
+
+def _cached_pack(module, device, build):
+    """build(device) -> packed weights of `module`, cached on the module until one of its tensors changes (stand-alone
+    Block / Mlp / Attention / PatchEmbed calls — modeling_pretrain composes Blocks this way, mp:8 — no longer re-fold and
+    re-cast their weights on every forward)."""
+    sig = (_weights_signature(module), str(device))
+    hit = module.__dict__.get("_stad_pack")
+    if hit is None or hit[0] != sig:
+        hit = (sig, build(device))
+        object.__setattr__(module, "_stad_pack", hit)
+    return hit[1]
 
 
 class _StadBackbone(nn.Module):
@@ -562,12 +614,15 @@ class VisionTransformer(_StadBackbone):
         return prep.run(inp, B, pe.num_patches, want=want)
 
     @torch.no_grad()
-    def forward_windows(self, frames, start=0, count=None, stride=1, frame_step=1, starts=None):
+    def forward_windows(self, frames, start=0, count=None, stride=1, frame_step=1, starts=None, reuse_tubelets=True):
         """Sliding-window inference straight from a resident frame buffer (ri:69-109, dota.py:204-223):
         frames [F, C, H, W] (fp32 or bf16, already normalised); frame t of window b is frames[start + b*stride +
         t*frame_step] (frame_step = orig_fps // target_fps, dataset/sequencing.py:45-58; 1 = consecutive frames).
         starts: optional int32 CUDA tensor [count] with the first frame of every window instead of start + b*stride —
         one batch can then hold windows of several videos laid end to end in `frames` (final_test, eff:385-463).
+        reuse_tubelets: embed every distinct tubelet of the batch once and assemble the overlapping windows from them
+        (stad_input.tubelet_reuse; the embedding is rounded to bf16 before the position add, so results match the clips
+        path within tolerance; False keeps them bit-identical to it).
         Returns (logits, probs), each [count, num_classes], without materialising the [count, C, T, H, W] clips."""
         self._check_supported()
         if frames.dim() != 4 or not frames.is_cuda:
@@ -596,7 +651,7 @@ class VisionTransformer(_StadBackbone):
         prep = self.prepare(frames.device)
         fb = prep.input_bf16(frames)
         inp = _lib.make_input(fb, _lib.STAD_IN_FRAMES, n_frames=F_, start=start, stride=stride, frame_step=frame_step,
-                              window_starts=starts)
+                              window_starts=starts, tubelet_reuse=reuse_tubelets)
         res = prep.run(inp, count, pe.num_patches, want=("logits", "probs"))
         return res["logits"], res["probs"]
 

@@ -115,13 +115,25 @@ def test_config2_vitb_sliding_window_video():
     sd = synth.make_state_dict("vit_base_patch16_224", seed=2)
     model = parity.build_classifier("vit_base_patch16_224", sd)
     frames = synth.make_video(100, seed=2).to(DEV)
+    from simple_tad_b200 import _lib
+    _lib.profile_enable(256)
     logits, probs = model.forward_windows(frames)
+    kinds = [(k, epi) for k, epi, *_ in _lib.profile_read()]
+    _lib.profile_enable(0)
     assert logits.shape == (85, 2)
-    parity.check_logits(logits, g["logits"], "config2 (85 windows)")
-    # same windows as explicit clips: identical kernels, identical tiles -> bit-identical scores
+    parity.check_logits(logits, g["logits"], "config2 (85 windows, tubelet embeddings shared between windows)")
+    # the default path embedded the 85 + 14 distinct tubelets once (one patch GEMM over 99 tubelets + the assemble
+    # kernel) instead of 85 x 8 of them
+    assert ("assemble", 2) in kinds, kinds
+    # without the reuse: same windows as explicit clips, identical kernels, identical tiles -> bit-identical scores
+    direct, _ = model.forward_windows(frames, reuse_tubelets=False)
+    direct = direct.clone()
     clips = synth.windows_from_video(synth.make_video(100, seed=2), start=0, count=85).to(DEV)
     logits2 = model(clips)
-    assert torch.equal(logits, logits2), "frame-buffer windows and materialised clips disagree"
+    assert torch.equal(direct, logits2), "frame-buffer windows and materialised clips disagree"
+    # the reuse path rounds the tubelet embedding to bf16 before the position add: one extra rounding, far inside the
+    # parity tolerance
+    assert float((logits - direct).abs().max()) <= 5e-3, float((logits - direct).abs().max())
 
 
 def test_config3_vitl_two_videos():

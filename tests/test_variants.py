@@ -107,10 +107,14 @@ def test_mvd_windows_equal_clips_gpu(name):
     frame-level): windows read out of the frame buffer == materialised clips, bit for bit."""
     model, x, info = parity.build_variant(name, device="cuda")
     frames = parity.synth.make_video(20, seed=3).to("cuda")
-    lw, pw = model.forward_windows(frames)
+    lw, pw = model.forward_windows(frames, reuse_tubelets=False)
+    lw = lw.clone()
     clips = parity.synth.windows_from_video(frames.cpu()).to("cuda")
-    lc = model(clips)
+    lc = model(clips).clone()
     assert torch.equal(lw, lc)
+    # default: tubelet embeddings shared between the overlapping windows (not with a class token) — one extra bf16 rounding
+    lr, _ = model.forward_windows(frames)
+    assert float((lr - lc).abs().max()) <= 5e-3
 
 
 @pytest.mark.gpu
@@ -136,7 +140,10 @@ def test_frame_step_windows_follow_the_sequencer_gpu():
     assert torch.equal(lg, ref.cpu())
     lg_all = runner.score_videos([frames, frames[:50]])
     plan2 = sequencing.window_plan(50, 30, 10, 16, step)
-    assert lg_all.shape[0] == plan.count + plan2.count and torch.equal(lg_all[: plan.count].cpu(), ref.cpu())
+    # the runner batches windows across video boundaries (one batch of 3 + 2 windows here): another batch size than
+    # `ref`, so equal within the parity tolerance rather than bit for bit
+    assert lg_all.shape[0] == plan.count + plan2.count
+    parity.check_logits(lg_all[: plan.count], ref, "frame-step windows, two videos in one batch")
     # batches of two windows: other tile shapes, so equal within the parity tolerance rather than bit for bit
     lg2, _ = SlidingWindowRunner(model, batch_windows=2, stride=step, frame_step=3).score_frames(frames)
     parity.check_logits(lg2, ref, "frame-step windows, batches of 2")
