@@ -74,16 +74,11 @@ int make_geom(const stad_dims* d, const stad_input* in, int B, PatchGeom* pg) {
   return STAD_OK;
 }
 
-// Up to this many rows the LN-folded GEMMs finish the LayerNorm statistics themselves (see run_blocks).
-// STAD_FOLD_STATS_MAX_ROWS overrides it (A/B measurements).
+// Up to this many rows the LN-folded GEMMs finish the LayerNorm statistics themselves (see run_blocks).  Measured
+// (profiles/r1c_fold_threshold_ab.txt): 34.4 k clips/s on the 16000-row DAPT batch at 8192 against 33.8 k / 34.0 k at
+// 32768 / 65536 — larger batches keep the 5 us finalize kernel.
 constexpr int kFoldStatsMaxRows = 8192;
-int fold_stats_max_rows() {
-  static const int v = [] {
-    const char* e = getenv("STAD_FOLD_STATS_MAX_ROWS");
-    return e ? atoi(e) : kFoldStatsMaxRows;
-  }();
-  return v;
-}
+int fold_stats_max_rows() { return kFoldStatsMaxRows; }
 
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 

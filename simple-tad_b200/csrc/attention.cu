@@ -85,10 +85,6 @@ __device__ int att_trace_n[4];
 #define ATT_T(i) do {} while (0)
 #endif
 
-#ifndef STAD_ATT_STAGGER
-#define STAD_ATT_STAGGER 1
-#endif
-
 struct AttArgs {
   bf16* out;
   int B, H, S;
@@ -549,7 +545,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // Phase offset between the two slots, re-established at the first tile of every two-slot unit: without it both
       // softmax warpgroups drift into lockstep (same phase of the tile at the same time), i.e. they fight for the
       // MUFU together and idle together.  Slot 1 starts when slot 0 has stored the first third of its first P tile.
-      const bool stagger = STAD_ATT_STAGGER && w.slots == 2;
+      const bool stagger = w.slots == 2;
       // loop-carried tile state, toggled instead of re-derived from g (keeps the per-tile glue short): score buffer
       // address (the two buffers differ in one address bit pattern: BKV = 0x60 and the slot base has those bits clear),
       // barrier addresses (8 bytes apart, 16-byte aligned pairs), barrier phase
@@ -578,17 +574,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       float m_ref = 0.f;  // reference max (log2 domain, already scaled): exact max of the unit's first tile
       float l_sum = 0.f;
-      const int n_full = (last_valid == BKV) ? n_kv : n_kv - 1;  // tiles with all 96 keys valid
+      // Loop bounds in ordinary registers (laundered through an empty asm): kept in uniform registers the compiler
+      // re-derives them from the kernel parameters at the top of EVERY tile (a chain of ~10 dependent uniform-datapath
+      // instructions and a constant-bank load on the critical path of the tile).
+      int n_tiles = n_kv;
+      int j_ragged = (last_valid == BKV) ? -1 : n_kv - 1;  // index of the ragged last tile, if any
+      asm volatile("" : "+r"(n_tiles), "+r"(j_ragged));
+      if (stagger && slot == 1) named_bar_sync(1, 2 * BQ);
 
-      for (int j = 0; j < n_kv; ++j, ++g, ph ^= buf, buf ^= 1, sp ^= BKV, s_bar ^= 8, p_bar ^= 8) {
+      for (int j = 0; j < n_tiles; ++j, ++g, ph ^= buf, buf ^= 1, sp ^= BKV, s_bar ^= 8, p_bar ^= 8) {
         ATT_T(7);
-        if (j == 0 && stagger && slot == 1) named_bar_sync(1, 2 * BQ);
         mbar_wait_a(s_bar, ph);
         tc_fence_after();
         ATT_T(0);
         uint32_t sv[3][32];
         float t_sum;
-        if (j > 0 && j < n_full) {
+        if (j != 0 && j != j_ragged) {
           // ---- steady state: full tile, lazy reference.  The second and third chunk are in flight while the first
           // is processed; P chunk i overwrites columns [16 i, +16), which lie in S chunk i / 2 (already in registers).
           const float neg_m = -m_ref;

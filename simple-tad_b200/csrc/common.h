@@ -40,7 +40,7 @@ int sm_count();  // SMs of the current device (cached)
 
 // Programmatic dependent launch: the kernel may start (prologue: barrier init, TMEM allocation, descriptor prefetch)
 // while the kernel before it in the stream is still draining; it must execute griddepcontrol.wait (pdl_wait() in
-// ptx.cuh) before it touches any global memory.  STAD_PDL=0 in the environment disables the attribute.
+// ptx.cuh) before it touches any global memory.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

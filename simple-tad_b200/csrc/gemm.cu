@@ -440,13 +440,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
 
-#if defined(STAD_GEMM_DBG) && STAD_GEMM_DBG >= 3
-        { float acc_ = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc_ += f[j];
-          if (acc_ == 123.456f) p.out[0] = __float2bfloat16(acc_); }
-        continue;  // DBG 3: TMEM load + math only
-#endif
         // staging buffer of this chunk is free (and holds the residual sub-tile, if any)
         uint8_t* buf;
         if constexpr (kPair) {
@@ -536,9 +529,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         named_bar_sync(1 + wg, 128);      // whole sub-tile staged
         if (lead_warp) {
           if (elect_one()) {  // deterministic: always the same lane, which owns the bulk async-groups
-#if !defined(STAD_GEMM_DBG) || STAD_GEMM_DBG < 1
             tma_store_2d(&tmap_out, buf, n0, tr.row0);  // rows beyond M (or beyond the box) are clipped by the TMA
-#endif
             tma_store_commit();
             prepare_buffer(ci + 1);
           }
@@ -619,42 +610,17 @@ int set_smem_pair() {
   return STAD_OK;
 }
 
-// 256 x 192 pair tiles are OFF by default: measured slower than the single-CTA 192-column tile on every shape that
-// would use them (ViT-S 6407 -> 6260 clips/s, full MAE forward 11.48 k -> 11.09 k; profiles/r1c_pair192_ab.txt) — with
-// K = 384 the mainloop is six k-blocks long and the tile is bound by its epilogue, which the pair does not shorten.
-// STAD_GEMM_PAIR_192=1 enables them (A/B measurements; results are identical, tests/kernel_checks.py::check_gemm_pair).
-bool pair_192_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("STAD_GEMM_PAIR_192");
-    return e && e[0] == '1';
-  }();
-  return on;
-}
-
-// STAD_GEMM_PAIR_MIN_K overrides the K from which the pair tile is used (development).
-int pair_min_k() {
-  static const int k = [] {
-    const char* e = getenv("STAD_GEMM_PAIR_MIN_K");
-    return e ? atoi(e) : 0;
-  }();
-  return k;
-}
-// STAD_GEMM_PAIR_ODD=0: shapes with an odd number of M-tiles stay on the single-CTA tile (A/B measurements).
-bool pair_odd_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("STAD_GEMM_PAIR_ODD");
-    return !(e && e[0] == '0');
-  }();
-  return on;
-}
-// STAD_GEMM_PAIR=0 in the environment keeps every GEMM on the single-CTA tile (A/B measurements).
-bool pair_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("STAD_GEMM_PAIR");
-    return !(e && e[0] == '0');
-  }();
-  return on;
-}
+// Which shapes run CTA-pair (256-row) tiles — settled by A/B measurements on the B200, recorded under profiles/:
+//   * 256 x 256 pair tiles for every GEMM with N % 256 == 0 (B = 64 ViT-B, single-CTA -> pair: qkv 259 -> 232 us, fc1
+//     387 -> 346, fc2 337 -> 318, proj 118 -> 118);
+//   * an odd number of M-tiles is padded with a virtual, fully clipped M-tile rather than falling back to single-CTA
+//     tiles (masked encoder 32.4 k -> 34.2 k clips/s, MVD + class token 2417 -> 2568; profiles/r1c_pair_odd_m_tiles_ab.txt);
+//   * 256 x 192 pair tiles (N = 384 / 1152: ViT-S, the MAE decoder) are NOT used: measured slower than the single-CTA
+//     192-column tile on every shape (ViT-S 6407 -> 6260 clips/s, full MAE forward 11.48 k -> 11.09 k;
+//     profiles/r1c_pair192_ab.txt) — with K = 384 the mainloop is six k-blocks long and the tile is bound by its
+//     epilogue, which the pair does not shorten.  The kernel stays generic in BN (tests/kernel_checks.py keeps the
+//     192-wide single-CTA tiles covered).
+constexpr bool kPairTiles192 = false;
 
 template <int EPI, bool kPatch>
 int set_smem_all_bn() {
@@ -793,9 +759,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
                         g.epi == (EPI_RESID | EPI_STATS);
   // (measured, B = 64 ViT-B, single-CTA -> pair tile with the warp-private epilogue: qkv 259 -> 232 us, fc1 387 -> 346,
   // fc2 337 -> 318, proj 118 -> 118)
-  const bool pair = pair_enabled() && !g.patch && (bn == 256 || (bn == 192 && pair_192_enabled())) &&
-                    (ka.m_tiles % 2 == 0 || pair_odd_enabled()) && pair_epi &&
-                    g.K >= pair_min_k() && ((ka.m_tiles + 1) / 2) * ka.n_tiles >= sm_count() / 2;
+  const bool pair = !g.patch && (bn == 256 || (bn == 192 && kPairTiles192)) && pair_epi &&
+                    ((ka.m_tiles + 1) / 2) * ka.n_tiles >= sm_count() / 2;
   {
     const uint64_t dims[2] = {(uint64_t)g.K, (uint64_t)g.N};
     const uint64_t strides[1] = {(uint64_t)g.K * 2};

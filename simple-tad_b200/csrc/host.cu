@@ -108,13 +108,7 @@ int fail(int code, const char* fmt, ...) {
 
 const char* last_error() { return g_err; }
 
-bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("STAD_PDL");
-    return !(e && e[0] == '0');
-  }();
-  return on;
-}
+bool pdl_enabled() { return true; }  // programmatic dependent launch on every GEMM / attention / finalize launch
 
 int sm_count() {
   if (g_sm_count == 0) {

@@ -388,25 +388,20 @@ STAD_DEVICE void mul2(float& d0, float& d1, float a0, float a1, float b0, float 
 }
 
 // GELU with the erf CDF (nn.GELU default, reference modeling_finetune.py:38/43) for a pair of values:
-//   x Phi(x),  Phi(x) = 0.5 (1 + erf(x / sqrt 2)) = sigmoid(2 u(x)),  u = atanh(erf(x / sqrt 2))
+//   x Phi(x),  Phi(x) = 0.5 (1 + erf(x / sqrt 2)) = sigmoid(2 u(x)) = 0.5 (1 + tanh u(x)),  u = atanh(erf(x / sqrt 2))
 // with u fitted by an odd degree-5 polynomial (weighted minimax over |x| <= 5.5; x^2 clamped at 64 keeps it monotone
-// beyond): max |error| 2.6e-5 for every x, two orders below the bf16 resolution of the stored result.  The sigmoid is
-// evaluated as 1 / (1 + 2^v), v = -2 log2(e) u(x): relative accuracy is kept in both tails (a tanh would lose the
-// negative one).  Packed FFMA2 / FMUL2 / FADD2 halve the issue slots of the fc1 epilogue, which is what bounds that GEMM.
-#ifndef STAD_GELU_TANH
-#define STAD_GELU_TANH 1
-#endif
+// beyond): max |error| of the fit 2.6e-5 for every x, two orders below the bf16 resolution of the stored result.
+// ONE MUFU op per element (MUFU.TANH; the earlier 1 / (1 + 2^v) form took EX2 + RCP): the epilogue of the fc1 GEMM is
+// what bounds that kernel and the MUFU is its busiest pipe (397 -> 372 us at B = 64).  tanh.approx has a relative error
+// of 2^-11, i.e. an absolute error <= |x| 2^-12 on x Phi(x): below the bf16 resolution of the stored value for x > -1.6
+// and <= 1e-3 in absolute terms for -4 < x < -1.6, where the exact result is within 0.08 of zero.  Packed FFMA2 / FMUL2
+// halve the issue slots.
 STAD_DEVICE float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 STAD_DEVICE void gelu_erf2(float& y0, float& y1, float x0, float x1) {
-#if STAD_GELU_TANH
-  // sigmoid(2u) = 0.5 (1 + tanh u): ONE MUFU op per element (MUFU.TANH) instead of two (EX2 + RCP); the epilogue of the
-  // fc1 GEMM is what bounds that kernel and the MUFU is its busiest pipe.  tanh.approx has a relative error of 2^-11,
-  // i.e. an absolute error <= |x| 2^-12 on x Phi(x): below the bf16 resolution of the stored value for x > -1.6 and
-  // <= 1e-3 in absolute terms for -4 < x < -1.6, where the exact result is within 0.08 of zero.
   constexpr float kC1 = 0.7975078480466281f, kC3 = 0.03700565355921658f, kC5 = -0.00035151798668820724f;
   float s0, s1, p0, p1, u0, u1, h0, h1;
   mul2(s0, s1, x0, x1, x0, x1);
@@ -417,18 +412,6 @@ STAD_DEVICE void gelu_erf2(float& y0, float& y1, float x0, float x1) {
   mul2(u0, u1, p0, p1, x0, x1);
   mul2(h0, h1, x0, x1, 0.5f, 0.5f);
   fma2(y0, y1, h0, h1, fast_tanh(u0), fast_tanh(u1), h0, h1);
-#else
-  constexpr float kB1 = -2.301121234893799f, kB3 = -0.10677574574947357f, kB5 = 0.0010142665123566985f;
-  float s0, s1, p0, p1, v0, v1, d0, d1;
-  mul2(s0, s1, x0, x1, x0, x1);
-  s0 = fminf(s0, 64.f);
-  s1 = fminf(s1, 64.f);
-  fma2(p0, p1, s0, s1, kB5, kB5, kB3, kB3);
-  fma2(p0, p1, p0, p1, s0, s1, kB1, kB1);
-  mul2(v0, v1, p0, p1, x0, x1);
-  add2(d0, d1, fast_exp2(v0), fast_exp2(v1), 1.f, 1.f);
-  mul2(y0, y1, x0, x1, fast_rcp(d0), fast_rcp(d1));
-#endif
 }
 
 }  // namespace stad

@@ -338,8 +338,8 @@ def check_gemm_pair():
         out.append(check_gemm(M, N, K, mode, seed=80 + len(out)))
     out.append(check_gemm_stats(16000, 768, 2304, 768, seed=9))
     out.append(check_gemm_stats(9600 - 91, 1024, 512, 4096, seed=10))
-    # 256 x 192 pair tiles (N = 384 / 1152: ViT-S, the MAE decoder): three 32-column chunks per epilogue warpgroup,
-    # i.e. the 2 + 1 store batching of the no-residual epilogues and the per-chunk residual ring
+    # N = 384 / 1152 (ViT-S, the MAE decoder) at pair-tile row counts: these run single-CTA 192-column tiles (256 x 192
+    # pair tiles measured slower, gemm.cu kPairTiles192): three 32-column chunks per epilogue warpgroup
     for M, N, K, mode in ((9472, 1152, 384, "plain"), (9472, 1152, 384, "ln"), (25088, 384, 384, "bias"),
                           (9472, 384, 1536, "resid"), (9600 - 37, 1152, 384, "ln_gelu"), (50176, 1152, 384, "ln"),
                           (50176, 384, 1536, "resid")):
