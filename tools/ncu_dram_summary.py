@@ -8,7 +8,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EPI = {"24, 1": "patch_embed", "1, 0": "qkv", "20, 0": "proj_or_fc2", "3, 0": "fc1", "4, 0": "fc2_last"}  # <256, EPI, patch(, pair)>
+EPI = {"24, 1": "patch_embed", "8, 1": "patch_embed", "1, 0": "qkv", "20, 0": "proj_or_fc2", "3, 0": "fc1", "4, 0": "fc2_last"}  # <256, EPI, patch(, pair)>
 
 
 def main():
