@@ -125,11 +125,13 @@ def save(name, **arrs):
 
 
 def gen_classifier(name, arch, B=None, video_T=None, n_videos=1, seed=0, peaky=1.0, use_ris=False, check_oracle=True,
-                   trained_like=False):
+                   trained_like=False, extra_clips_seed=None):
     D, depth, heads = synth.ARCHS[arch]
     sd = (synth.make_trained_like_state_dict(arch, seed=seed) if trained_like else
           synth.make_state_dict(arch, seed=seed, peaky=peaky))
-    if video_T is None:
+    if video_T is None and extra_clips_seed is not None:
+        x = torch.cat([synth.make_clips(8, seed=seed), synth.make_clips(B - 8, seed=extra_clips_seed)])
+    elif video_T is None:
         x = synth.make_clips(B, seed=seed)
     else:
         x = torch.cat([synth.windows_from_video(synth.make_video(video_T, seed=seed + v)) for v in range(n_videos)])
@@ -417,6 +419,12 @@ def main():
         gen_pretrain("c4_mae_vitb_b2", "vit_base_patch16_224", B=2, seed=6, decoder_depth=4)
     if on("c5"):
         gen_classifier("c5_vitb_b8", "vit_base_patch16_224", B=8, seed=5)
+    if on("c5big"):
+        # the bench batch: all 64 clips of a B = 64 forward against the reference (the first 8 are c5_vitb_b8's clips)
+        gen_classifier("c5_vitb_b64", "vit_base_patch16_224", B=64, seed=5, check_oracle=False, extra_clips_seed=50)
+    if on("c3big"):
+        # config 3 at a size that exercises several batches: ViT-L, 2 videos x 47 frames = 2 x 32 windows
+        gen_classifier("c3_vitl_2x47", "vit_large_patch16_224", video_T=47, n_videos=2, seed=3, check_oracle=False)
     if on("trained"):
         # trained-like statistics (outlier channels, shifted rows, wide LayerNorm gamma, layer scale): see
         # synth.make_trained_like_state_dict

@@ -17,6 +17,10 @@
 //                  so S_{j+1} is complete long before the softmax warps finish tile j: inside a unit they never wait
 //                  for the tensor core.  Q K_{j+2}^T re-uses the buffer of S_j / P_j; it is issued after P_j V_j by
 //                  the same thread and tcgen05.mma executes in issue order, so no barrier is needed between them.
+//                  The tiles of consecutive units form ONE stream: the first two Q K^T of unit u+1 are issued behind
+//                  the last two P V of unit u (Q tiles are double-buffered per slot for this), so the softmax warps
+//                  find S_0 of the next unit complete when they finish a unit — with two K/V tiles per unit (S = 160,
+//                  the masked encoder) the hand-over at the unit boundary was most of the kernel.
 //   warps 0..3   : softmax of slot 0, one query row per thread: tcgen05.ld S_j, exp2(s*c - m) (FFMA2 + MUFU.EX2, one
 //   warps 4..7   : softmax of slot 1   pair in four on the FMA pipe), row sum (FADD2), P_j (bf16) -> TMEM.
 //                  LAZY REFERENCE MAX: the exact row max is taken on the first tile of a unit only.  Later tiles use
@@ -48,12 +52,14 @@ constexpr int KV_STAGES = 5;
 constexpr int Q_BYTES = BQ * HD * 2;    // 16 KB
 constexpr int KV_BYTES = BKV * HD * 2;  // 12 KB: every K / V tile
 constexpr int ATT_THREADS = 512;  // warpgroups 0, 1: softmax slots; 2: epilogue; 3: TMA + 2 MMA issuers (+1 idle warp)
-constexpr int LSUM_BYTES = 2 * BQ * 4;  // row sums handed from the softmax warps to the epilogue warps
+constexpr int LSUM_BYTES = 3 * BQ * 4;  // row sums handed from the softmax warps to the epilogue warps: [slot][row], then
+                                        // the reference maxima of a key-split unit's (key part, query) pairs
 // Key-split tail units (see Unit::split): the four partial O rows of a query are combined through this scratch,
 // [key part][column][query] fp32 (query fastest: conflict-free for writers and readers)
 constexpr int SPLIT_ROWS = 32;
 constexpr int SPLIT_SCRATCH_BYTES = 4 * HD * SPLIT_ROWS * 4;
-constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * KV_STAGES * KV_BYTES + LSUM_BYTES + 512 + SPLIT_SCRATCH_BYTES + 1024;
+constexpr int Q_BUFS = 2;           // Q tiles per slot: unit u+1's Q is resident while unit u is still being multiplied
+constexpr int SMEM_BYTES = 2 * Q_BUFS * Q_BYTES + 2 * KV_STAGES * KV_BYTES + LSUM_BYTES + 512 + SPLIT_SCRATCH_BYTES + 1024;
 // Warp roles.  The single-thread TMA / MMA issuers sit in the HIGHEST warps: the sub-partition arbiter favours high warp
 // ids, and an issuer that has to queue behind two always-ready softmax warps paces the whole kernel (measured: ~135
 // clk per tcgen05.mma issue and ~350 clk per already-complete mbarrier wait when the issuers were warps 0-2).
@@ -70,8 +76,8 @@ constexpr float kRescaleThreshold = 8.0f;            // log2 units; key-split ta
 // att_trace (development builds only; read through stad_debug_read_att_trace, see tools/att_trace.py).
 #ifdef STAD_ATT_TRACE
 constexpr int kTraceCap = 2048;
-__device__ unsigned long long att_trace[4][kTraceCap];
-__device__ int att_trace_n[4];
+__device__ unsigned long long att_trace[6][kTraceCap];
+__device__ int att_trace_n[6];
 #define ATT_EV(role, tag)                                                                    \
   do {                                                                                       \
     if (blockIdx.x == 0 && tr_n < kTraceCap && (threadIdx.x & 31) == 0) {                    \
@@ -126,14 +132,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* smem_q = smem;                                   // [2][16 KB]
-  uint8_t* smem_k = smem_q + 2 * Q_BYTES;                   // [KV_STAGES][12 KB]
+  uint8_t* smem_q = smem;                                   // [2 slots][Q_BUFS][16 KB]
+  uint8_t* smem_k = smem_q + 2 * Q_BUFS * Q_BYTES;          // [KV_STAGES][12 KB]
   uint8_t* smem_v = smem_k + KV_STAGES * KV_BYTES;          // [KV_STAGES][12 KB]
   float* lsum_smem = reinterpret_cast<float*>(smem_v + KV_STAGES * KV_BYTES);  // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + KV_STAGES * KV_BYTES + LSUM_BYTES);
-  uint64_t* q_full = bars;                   // [2]  TMA -> MMA
-  uint64_t* q_free = q_full + 2;             // [2]  MMA (last Q K^T of the unit) -> TMA
-  uint64_t* k_full = q_free + 2;             // [KV_STAGES]
+  uint64_t* q_full = bars;                   // [2 slots][Q_BUFS]  TMA -> MMA
+  uint64_t* q_free = q_full + 2 * Q_BUFS;    // [2 slots][Q_BUFS]  MMA (last Q K^T of the unit) -> TMA
+  uint64_t* k_full = q_free + 2 * Q_BUFS;    // [KV_STAGES]
   uint64_t* k_free = k_full + KV_STAGES;     // [KV_STAGES]
   uint64_t* v_full = k_free + KV_STAGES;     // [KV_STAGES]
   uint64_t* v_free = v_full + KV_STAGES;     // [KV_STAGES]
@@ -142,7 +148,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* o_full = p_full + 4;             // [2]  MMA -> softmax / epilogue: P_j V_j complete
   uint64_t* l_ready = o_full + 2;            // [2]  softmax (128 threads) -> epilogue: unit done, row sums in smem
   uint64_t* o_free = l_ready + 2;            // [2]  epilogue (4 warps) -> MMA: O has been read, next unit may overwrite
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* o_done = o_free + 2;             // [2]  MMA -> epilogue: the LAST P V of a unit is complete (one phase per unit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
   float* split_scratch = reinterpret_cast<float*>(smem_v + KV_STAGES * KV_BYTES + LSUM_BYTES + 512);
 
   // warp index through a shuffle: the compiler then knows every value derived from it is warp-uniform (uniform
@@ -153,19 +160,29 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int units_per_head = (n_q + 1) / 2;
   const int total_units = p.B * p.H * units_per_head;
   const int n_kv = (p.S + BKV - 1) / BKV;
-  const int last_valid = p.S - (n_kv - 1) * BKV;   // valid keys of the last K/V tile, 1..96
-  const int last_chunks = (last_valid + 31) >> 5;  // 32-column chunks of the last tile that hold any valid key
+  // The keys beyond the last multiple of 96 form a short ("ragged") tile.  It is processed FIRST (tile 0 of every
+  // unit), the full tiles follow: the first tile of a unit is special anyway (it takes the exact row max that becomes
+  // the lazy reference, with all its exps on the MUFU), and a separate ragged tile at the end costs nearly a full
+  // tile's latency chain for a third of the work (S = 1568: 32 keys).  Folding the two special tiles into one short
+  // first tile leaves 16 steady-state tiles per unit.
+  const int last_valid = p.S - (n_kv - 1) * BKV;   // valid keys of the ragged tile, 1..96 (96: no ragged tile)
+  const int last_chunks = (last_valid + 31) >> 5;  // its 32-column chunks that hold any valid key
+  // first key of tile j
+  auto kv_row = [&](int j) { return last_valid == BKV ? j * BKV : (j == 0 ? (n_kv - 1) * BKV : (j - 1) * BKV); };
 
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_kv);
     tma_prefetch_desc(&tmap_q32);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 2 * Q_BUFS; ++s) {
       mbar_init(&q_full[s], 1);
       mbar_init(&q_free[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&o_full[s], 1);
       mbar_init(&l_ready[s], BQ);
       mbar_init(&o_free[s], 4);
+      mbar_init(&o_done[s], 1);
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&s_full[s], 1);
@@ -207,7 +224,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       };
       auto load_k = [&](int j, int b, int col_k) {
         mbar_wait(&k_free[kst], kph ^ 1);
-        load_tile(&tmap_kv, &k_full[kst], smem_k + kst * KV_BYTES, KV_BYTES, col_k, j * BKV, b);
+        load_tile(&tmap_kv, &k_full[kst], smem_k + kst * KV_BYTES, KV_BYTES, col_k, kv_row(j), b);
         if (++kst == KV_STAGES) {
           kst = 0;
           kph ^= 1;
@@ -218,30 +235,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int col_q = w.h * HD;
         const int col_k = (p.H + w.h) * HD;
         const int col_v = (2 * p.H + w.h) * HD;
-        mbar_wait(&q_free[0], (ucnt0 & 1) ^ 1);
+        // Q tile of slot s for its n-th unit -> buffer n % Q_BUFS (free once the last Q K^T of unit n - Q_BUFS is done)
+        const uint32_t qb0 = ucnt0 % Q_BUFS;
+        uint8_t* q0_dst = smem_q + qb0 * Q_BYTES;
+        mbar_wait(&q_free[qb0], ((ucnt0 / Q_BUFS) & 1) ^ 1);
         if (w.split) {
           // the same 32 query rows into each of the four 32-row groups of the tile (4 KB apart in the swizzled layout)
           if (elect_one()) {
-            mbar_arrive_expect_tx(&q_full[0], Q_BYTES);
+            mbar_arrive_expect_tx(&q_full[qb0], Q_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tma_load_3d(smem_q + k * (SPLIT_ROWS * HD * 2), &tmap_q32, &q_full[0], col_q, w.q0, w.b);
+              tma_load_3d(q0_dst + k * (SPLIT_ROWS * HD * 2), &tmap_q32, &q_full[qb0], col_q, w.q0, w.b);
           }
           __syncwarp();
         } else {
-          load_tile(&tmap_q, &q_full[0], smem_q, Q_BYTES, col_q, w.q0, w.b);
+          load_tile(&tmap_q, &q_full[qb0], q0_dst, Q_BYTES, col_q, w.q0, w.b);
         }
         ++ucnt0;
         if (w.slots > 1) {
-          mbar_wait(&q_free[1], (ucnt1 & 1) ^ 1);
-          load_tile(&tmap_q, &q_full[1], smem_q + Q_BYTES, Q_BYTES, col_q, w.q0 + BQ, w.b);
+          const uint32_t qb1 = ucnt1 % Q_BUFS;
+          mbar_wait(&q_free[Q_BUFS + qb1], ((ucnt1 / Q_BUFS) & 1) ^ 1);
+          load_tile(&tmap_q, &q_full[Q_BUFS + qb1], smem_q + (Q_BUFS + qb1) * Q_BYTES, Q_BYTES, col_q, w.q0 + BQ, w.b);
           ++ucnt1;
         }
         load_k(0, w.b, col_k);
         for (int j = 0; j < n_kv; ++j) {
           if (j + 1 < n_kv) load_k(j + 1, w.b, col_k);
           mbar_wait(&v_free[vst], vph ^ 1);
-          load_tile(&tmap_kv, &v_full[vst], smem_v + vst * KV_BYTES, KV_BYTES, col_v, j * BKV, w.b);
+          load_tile(&tmap_kv, &v_full[vst], smem_v + vst * KV_BYTES, KV_BYTES, col_v, kv_row(j), w.b);
           if (++vst == KV_STAGES) {
             vst = 0;
             vph ^= 1;
@@ -254,97 +275,141 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // The whole warp runs the (warp-uniform) control flow and waits; one elected lane issues tcgen05.mma / commit.
       // Both slots read the same K / V ring stages; a stage is released by two arrivals (one per slot; in a one-slot
       // unit the slot-0 warp commits twice).
+      // The K/V tiles of all units of this slot are ONE stream t = 0, 1, 2, ...: tile t uses score buffer t & 1, and
+      // Q K_{t+2}^T is issued right behind P_t V_t whether or not tile t + 2 belongs to the same unit.  Two cursors
+      // walk the unit list: `qk` (two tiles ahead) and `pv`.
       const int slot = warp - kMmaWarp0;
 #ifdef STAD_ATT_TRACE
       int tr_n = 0;
 #endif
       constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);   // P from TMEM (K-major), V MN-major (d contiguous)
       constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major
-      const uint64_t desc_q = make_smem_desc_sw128(smem_u32(smem_q + slot * Q_BYTES), 16, 1024);
+      const uint64_t desc_q_base = make_smem_desc_sw128(smem_u32(smem_q + slot * Q_BUFS * Q_BYTES), 16, 1024);
       const uint32_t tmem_slot_base = tmem_base + slot * SLOT_COLS;
       const uint32_t tmem_o = tmem_slot_base + O_COL;
-      uint32_t kc = 0, vc = 0;  // K / V tiles consumed so far (ring position = count % stages)
-      uint32_t g = 0;           // tiles completed by this slot: tile g uses score buffer g & 1 for the (g >> 1)-th time
-      uint32_t ucnt = 0;        // units started by this slot (phase of q_full / q_free / o_free)
-
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const Unit w = decode_unit(u, units_per_head, p.H, p.S);
-        if (slot >= w.slots) {  // one-slot unit: slot 1 sits it out but stays in step with the rings
-          kc += n_kv;
-          vc += n_kv;
-          continue;
-        }
-        const bool solo = w.slots == 1;
-        // S_j = Q K_j^T into score buffer (g + j) & 1; releases the K stage
-        auto issue_qk = [&](int j) {
-          const uint32_t kst = kc % KV_STAGES;
-          mbar_wait(&k_full[kst], (kc / KV_STAGES) & 1);
-          tc_fence_after();
-          const uint32_t buf = (g + j) & 1;
-          const bool last = j + 1 == n_kv;
-          ATT_EV(2 + slot, 20);
-          if (elect_one()) {
-            const uint64_t desc_k = make_smem_desc_sw128(smem_u32(smem_k + kst * KV_BYTES), 16, 1024);
-            const uint32_t tmem_s = tmem_slot_base + buf * BKV;
-            if (!last || last_valid == BKV) {
-#pragma unroll
-              for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc_qk, k != 0);
-            } else {  // ragged last tile: only the 32-key chunks that hold a valid key
-              const uint32_t idesc = make_idesc_bf16(BQ, static_cast<uint32_t>(last_chunks * 32), 0, 0);
-#pragma unroll
-              for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc, k != 0);
-            }
-            umma_commit(&s_full[slot * 2 + buf]);
-            if (last) umma_commit(&q_free[slot]);
-            umma_commit(&k_free[kst]);
-            if (solo) umma_commit(&k_free[kst]);
+      struct Cursor {
+        int u;         // unit index (this CTA's units: blockIdx.x, + gridDim.x, ...)
+        int j;         // K/V tile within the unit
+        uint32_t t;    // tiles of this slot before (u, j): score buffer t & 1, its (t >> 1)-th use
+        uint32_t n;    // units of this slot before u (Q buffer n % Q_BUFS; phase of o_free)
+        uint32_t ring; // K (qk cursor) / V (pv cursor) tiles of the CTA before (u, j), skipped units included
+        bool solo;     // one-slot unit
+        bool gap;      // the cursor skipped at least one unit (one this slot sits out) on its way to u
+      };
+      // position the cursor on the next unit (from c.u on) this slot takes part in; false: no more units
+      auto seek = [&](Cursor& c) {
+        c.gap = false;
+        while (c.u < total_units) {
+          const Unit w = decode_unit(c.u, units_per_head, p.H, p.S);
+          if (slot < w.slots) {
+            c.solo = w.slots == 1;
+            return true;
           }
-          __syncwarp();
-          ATT_EV(2 + slot, 21);
-          ++kc;
-        };
-        // O (+)= P_j V_j.  V tile: one 128-byte row per key -> MN-major B operand; 16 keys = 2 x 1024 B per MMA.
-        auto issue_pv = [&](int j) {
-          const uint32_t vst = vc % KV_STAGES;
-          mbar_wait(&v_full[vst], (vc / KV_STAGES) & 1);
-          if (j == 0 && ucnt > 0) mbar_wait(&o_free[slot], (ucnt - 1) & 1);  // epilogue has read the previous unit's O
-          const uint32_t buf = (g + j) & 1;
-          ATT_EV(2 + slot, 22);
-          mbar_wait(&p_full[slot * 2 + buf], ((g + j) >> 1) & 1);
-          tc_fence_after();
-          ATT_EV(2 + slot, 23);
-          const int ksteps = (j + 1 == n_kv) ? last_chunks * 2 : BKV / 16;
-          if (elect_one()) {
-            const uint64_t desc_v = make_smem_desc_sw128(smem_u32(smem_v + vst * KV_BYTES), 0, 1024);
-            const uint32_t tmem_p = tmem_slot_base + buf * BKV;
-            if (ksteps == BKV / 16) {
-#pragma unroll
-              for (int k = 0; k < BKV / 16; ++k)
-                umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, (j != 0 || k != 0) ? 1u : 0u);
-            } else {
-              for (int k = 0; k < ksteps; ++k)
-                umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, (j != 0 || k != 0) ? 1u : 0u);
-            }
-            umma_commit(&o_full[slot]);
-            umma_commit(&v_free[vst]);
-            if (solo) umma_commit(&v_free[vst]);
-          }
-          __syncwarp();
-          ATT_EV(2 + slot, 24);
-          ++vc;
-        };
-
-        mbar_wait(&q_full[slot], ucnt & 1);
-        issue_qk(0);
-        if (n_kv > 1) issue_qk(1);
-        for (int j = 0; j < n_kv; ++j) {
-          issue_pv(j);
-          if (j + 2 < n_kv) issue_qk(j + 2);
+          c.ring += n_kv;  // one-slot unit: slot 1 sits it out but stays in step with the rings
+          c.u += gridDim.x;
+          c.gap = true;
         }
-        g += n_kv;
-        ++ucnt;
+        return false;
+      };
+      auto advance = [&](Cursor& c) {
+        ++c.t;
+        ++c.ring;
+        if (++c.j < n_kv) return true;
+        c.j = 0;
+        ++c.n;
+        c.u += gridDim.x;
+        return seek(c);
+      };
+      // S = Q K_j^T of the qk cursor's tile into score buffer t & 1; releases the K stage (and Q after the unit's last tile)
+      auto issue_qk = [&](const Cursor& c) {
+        const uint32_t qb = c.n % Q_BUFS;
+        if (c.j == 0) mbar_wait(&q_full[slot * Q_BUFS + qb], (c.n / Q_BUFS) & 1);
+        const uint32_t kst = c.ring % KV_STAGES;
+        mbar_wait(&k_full[kst], (c.ring / KV_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t buf = c.t & 1;
+        const bool last = c.j + 1 == n_kv;
+        ATT_EV(2 + slot, 20);
+        if (elect_one()) {
+          const uint64_t desc_q = desc_q_base + static_cast<uint64_t>(qb * (Q_BYTES >> 4));
+          const uint64_t desc_k = make_smem_desc_sw128(smem_u32(smem_k + kst * KV_BYTES), 16, 1024);
+          const uint32_t tmem_s = tmem_slot_base + buf * BKV;
+          if (c.j != 0 || last_valid == BKV) {
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc_qk, k != 0);
+          } else {  // ragged tile: only the 32-key chunks that hold a valid key
+            const uint32_t idesc = make_idesc_bf16(BQ, static_cast<uint32_t>(last_chunks * 32), 0, 0);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc, k != 0);
+          }
+          umma_commit(&s_full[slot * 2 + buf]);
+          if (last) umma_commit(&q_free[slot * Q_BUFS + qb]);
+          umma_commit(&k_free[kst]);
+          if (c.solo) umma_commit(&k_free[kst]);
+        }
+        __syncwarp();
+        ATT_EV(2 + slot, 21);
+      };
+      // O (+)= P_j V_j of the pv cursor's tile.  V tile: one 128-byte row per key -> MN-major B operand; 16 keys =
+      // 2 x 1024 B per MMA.
+      auto issue_pv = [&](const Cursor& c) {
+        const uint32_t vst = c.ring % KV_STAGES;
+        mbar_wait(&v_full[vst], (c.ring / KV_STAGES) & 1);
+        if (c.j == 0 && c.n > 0) mbar_wait(&o_free[slot], (c.n - 1) & 1);  // epilogue has read the previous unit's O
+        const uint32_t buf = c.t & 1;
+        ATT_EV(2 + slot, 22);
+        mbar_wait(&p_full[slot * 2 + buf], (c.t >> 1) & 1);
+        tc_fence_after();
+        ATT_EV(2 + slot, 23);
+        const int ksteps = (c.j == 0) ? last_chunks * 2 : BKV / 16;  // (no ragged tile: last_chunks * 2 = BKV / 16)
+        if (elect_one()) {
+          const uint64_t desc_v = make_smem_desc_sw128(smem_u32(smem_v + vst * KV_BYTES), 0, 1024);
+          const uint32_t tmem_p = tmem_slot_base + buf * BKV;
+          if (ksteps == BKV / 16) {
+#pragma unroll
+            for (int k = 0; k < BKV / 16; ++k)
+              umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, (c.j != 0 || k != 0) ? 1u : 0u);
+          } else {
+            for (int k = 0; k < ksteps; ++k)
+              umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, (c.j != 0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit(&o_full[slot]);
+          if (c.j + 1 == n_kv) umma_commit(&o_done[slot]);
+          umma_commit(&v_free[vst]);
+          if (c.solo) umma_commit(&v_free[vst]);
+        }
+        __syncwarp();
+        ATT_EV(2 + slot, 24);
+      };
+
+      Cursor qk = {static_cast<int>(blockIdx.x), 0, 0u, 0u, 0u, false, false};
+      Cursor pv = qk;
+      bool more_qk = seek(qk);
+      bool more_pv = seek(pv);
+      while (more_pv) {
+        // Up to two score tiles ahead of the P V stream.  NOT across a unit this slot sits out: the K tiles of that
+        // unit come first in the ring and are loaded only as V stages become free, and the V stages of this slot's
+        // current unit are released by P V this warp would be holding back while it waits for the K tile after the
+        // gap (deadlock).  Behind a gap the slot finishes its unit first, as it would without look-ahead.
+        while (more_qk && qk.t - pv.t < 2 && (!qk.gap || qk.u == pv.u)) {
+          issue_qk(qk);
+          more_qk = advance(qk);
+        }
+        issue_pv(pv);
+        more_pv = advance(pv);
       }
     }
+#ifdef STAD_ATT_TRACE
+    else {  // warp 15 (idle in product builds): when does each S tile of slot 0 really complete?
+      int tr_n = 0;
+      uint32_t t = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x)
+        for (int j = 0; j < n_kv; ++j, ++t) {
+          mbar_wait(&s_full[t & 1], (t >> 1) & 1);
+          ATT_EV(4, 30 + (t & 1));
+        }
+    }
+#endif
   } else if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     // ------------------------------------------------------------------ epilogue warps: O / l -> bf16 -> global
@@ -352,16 +417,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint32_t gs[2] = {0, 0};    // tiles completed per slot
     uint32_t ucs[2] = {0, 0};   // units completed per slot
+#ifdef STAD_ATT_TRACE
+    int tr_n = 0;
+#define ATT_E(i) do { if (quarter == 0 && slot == 0) ATT_EV(5, i); } while (0)
+#else
+#define ATT_E(i) do {} while (0)
+#endif
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const Unit w = decode_unit(u, units_per_head, p.H, p.S);
 #pragma unroll
       for (int slot = 0; slot < 2; ++slot) {
         if (slot >= w.slots) continue;
-        gs[slot] += n_kv;
-        mbar_wait(&l_ready[slot], ucs[slot] & 1);          // every softmax thread of the slot finished the unit
-        mbar_wait(&o_full[slot], (gs[slot] - 1) & 1);      // last P V of the unit
+        // every softmax thread of the slot has finished the unit, and its last P V is complete.  (o_done, not the
+        // per-tile o_full: the softmax warps can be through with a short unit before its FIRST P V has completed, and a
+        // parity wait for tile n while tile n - 1 is still pending falls through.)
+        ATT_E(39);
+        mbar_wait(&l_ready[slot], ucs[slot] & 1);
+        ATT_E(40);
+        mbar_wait(&o_done[slot], ucs[slot] & 1);
+        ATT_E(41);
         tc_fence_after();
         ++ucs[slot];
         const uint32_t o_addr = lane_addr + slot * SLOT_COLS + O_COL;
@@ -371,7 +446,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           float mk[4], M = -INFINITY;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            mk[k] = lsum_smem[BQ + k * 32 + lane];
+            mk[k] = lsum_smem[2 * BQ + k * 32 + lane];
             M = fmaxf(M, mk[k]);
           }
           float L = 0.f;
@@ -433,6 +508,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_free[slot]);
+            ATT_E(42);
           }
           if (warp_valid && row < p.S) {
 #pragma unroll
@@ -458,9 +534,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t o_addr = slot_addr + O_COL;
     const float c = p.scale_log2;
     uint32_t g = 0;  // tiles completed by this slot (buffer g & 1, its (g >> 1)-th use; o_full phase g)
+    uint32_t un = 0;  // units completed by this slot
 #ifdef STAD_ATT_TRACE
     int tr_n = 0;
 #endif
+    // End of a unit: row sum (and, key-split units, the reference max) to the epilogue warps.  The scores of the next
+    // unit are computed ahead of time (see the MMA issuers), so with few K/V tiles per unit these warps can finish
+    // unit n before the epilogue warps have taken unit n - 1: wait until they have (o_free: O and the row sums read).
+    // (With three or more tiles per unit the wait is implied: S of the unit's last tile exists only after the issuer
+    // has started the unit's first P V, for which it waited on the same o_free phase itself.)
+    auto hand_over = [&](float l, float m, bool with_max) {
+      if (un > 0 && n_kv < 3) mbar_wait(&o_free[slot], (un - 1) & 1);
+      lsum_smem[slot * BQ + r] = l;
+      if (with_max) lsum_smem[2 * BQ + r] = m;
+      mbar_arrive(&l_ready[slot]);
+      ++un;
+    };
 
     // Rescale of this thread's O row (rare: slow path of the lazy reference / growth in a key-split unit).
     auto rescale_o = [&](float alpha) {
@@ -496,7 +585,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         for (int j = 0; j < n_kv; ++j, ++g) {
           const uint32_t buf = g & 1;
           const uint32_t sp = slot_addr + buf * BKV;
-          const int valid = ((j + 1 < n_kv) ? BKV : last_valid) - quarter * 32;  // keys of this tile in my chunk
+          const int valid = (j == 0 ? last_valid : BKV) - quarter * 32;  // keys of this tile in my chunk
           mbar_wait(&s_full[slot * 2 + buf], (g >> 1) & 1);
           tc_fence_after();
           uint32_t pk[16];
@@ -536,16 +625,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
           publish_p(p_full_a + buf * 8);
         }
-        lsum_smem[r] = l_sum;        // partial sum of (query lane, key part)
-        lsum_smem[BQ + r] = m_ref;   // its reference max (-inf: this part never saw a key); slot 1's half is idle here
-        mbar_arrive(&l_ready[slot]);
+        // partial sum of (query lane, key part) and its reference max (-inf: this part never saw a key)
+        hand_over(l_sum, m_ref, true);
         continue;
       }
       const int row0 = w.q0 + slot * BQ;
       // Phase offset between the two slots, re-established at the first tile of every two-slot unit: without it both
       // softmax warpgroups drift into lockstep (same phase of the tile at the same time), i.e. they fight for the
       // MUFU together and idle together.  Slot 1 starts when slot 0 has stored the first third of its first P tile.
-      const bool stagger = w.slots == 2;
+      // (Only with >= KV_STAGES tiles per unit: the shared K ring then keeps slot 0 from reaching the next unit's arrive
+      // before slot 1 has passed this unit's sync, so the arrive / sync counts of the named barrier cannot interleave.)
+      const bool stagger = w.slots == 2 && n_kv >= KV_STAGES;
       // loop-carried tile state, toggled instead of re-derived from g (keeps the per-tile glue short): score buffer
       // address (the two buffers differ in one address bit pattern: BKV = 0x60 and the slot base has those bits clear),
       // barrier addresses (8 bytes apart, 16-byte aligned pairs), barrier phase
@@ -568,8 +658,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           s_bar ^= 8;
           p_bar ^= 8;
         }
-        lsum_smem[slot * BQ + r] = 1.f;
-        mbar_arrive(&l_ready[slot]);
+        hand_over(1.f, 0.f, false);
         continue;
       }
       float m_ref = 0.f;  // reference max (log2 domain, already scaled): exact max of the unit's first tile
@@ -578,8 +667,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // re-derives them from the kernel parameters at the top of EVERY tile (a chain of ~10 dependent uniform-datapath
       // instructions and a constant-bank load on the critical path of the tile).
       int n_tiles = n_kv;
-      int j_ragged = (last_valid == BKV) ? -1 : n_kv - 1;  // index of the ragged last tile, if any
-      asm volatile("" : "+r"(n_tiles), "+r"(j_ragged));
+      asm volatile("" : "+r"(n_tiles));
       if (stagger && slot == 1) named_bar_sync(1, 2 * BQ);
 
       for (int j = 0; j < n_tiles; ++j, ++g, ph ^= buf, buf ^= 1, sp ^= BKV, s_bar ^= 8, p_bar ^= 8) {
@@ -589,7 +677,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         ATT_T(0);
         uint32_t sv[3][32];
         float t_sum;
-        if (j != 0 && j != j_ragged) {
+        if (j != 0) {
           // ---- steady state: full tile, lazy reference.  The second and third chunk are in flight while the first
           // is processed; P chunk i overwrites columns [16 i, +16), which lie in S chunk i / 2 (already in registers).
           const float neg_m = -m_ref;
@@ -611,22 +699,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           t_sum = (a0 + a1) + (b0 + b1);
           ATT_T(3);
         } else {
-          // ---- first tile of the unit (exact max -> reference) and / or ragged last tile (masked, fewer chunks)
-          const int ncols = (j + 1 < n_kv) ? BKV : last_valid;  // valid keys of this tile
+          // ---- first tile of the unit: the ragged tile if there is one (masked, fewer chunks); exact max -> reference
+          const int ncols = last_valid;  // valid keys of this tile
           const int nch = (ncols + 31) >> 5;
 #pragma unroll
           for (int q = 0; q < 3; ++q)
             if (q < nch) tmem_ld32(sp + q * 32, sv[q]);
+          float mx = -INFINITY;
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             if (q < nch) {
               tmem_ld_wait32(sv[q]);
               if (ncols - q * 32 < 32) mask_from(sv[q], ncols - q * 32);
-            } else {
-              mask_from(sv[q], 0);
+              mx = fmaxf(mx, chunk_max(sv[q]));
             }
           }
-          if (j == 0) m_ref = c * max3(chunk_max(sv[0]), chunk_max(sv[1]), chunk_max(sv[2]));
+          m_ref = c * mx;
           const float neg_m = -m_ref;
           float a0 = 0.f, a1 = 0.f;
 #pragma unroll
@@ -635,7 +723,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               uint32_t pk[16];
               exp_chunk<false>(sv[q], c, neg_m, a0, a1, pk);
               tmem_st16(sp + q * 16, pk);
-              if (q == 0 && j == 0 && stagger && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
+              if (q == 0 && stagger && slot == 0) asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
             }
           }
           t_sum = a0 + a1;
@@ -670,8 +758,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         ATT_T(5);
       }
       // ---- hand the row sum to the epilogue warps and go on with the next unit
-      lsum_smem[slot * BQ + r] = l_sum;
-      mbar_arrive(&l_ready[slot]);
+      hand_over(l_sum, 0.f, false);
     }
   }
 
@@ -689,9 +776,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #ifdef STAD_ATT_TRACE
 extern "C" __attribute__((visibility("default"))) int stad_debug_read_att_trace(unsigned long long* out, int* counts) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, att_trace, sizeof(unsigned long long) * 4 * kTraceCap);
-  cudaMemcpyFromSymbol(counts, att_trace_n, sizeof(int) * 4);
-  int zero[4] = {0, 0, 0, 0};
+  cudaMemcpyFromSymbol(out, att_trace, sizeof(unsigned long long) * 6 * kTraceCap);
+  cudaMemcpyFromSymbol(counts, att_trace_n, sizeof(int) * 6);
+  int zero[6] = {0, 0, 0, 0, 0, 0};
   cudaMemcpyToSymbol(att_trace_n, zero, sizeof(zero));
   return kTraceCap;
 }

@@ -148,6 +148,21 @@ def test_config3_vitl_two_videos():
     parity.check_logits(torch.cat(outs), g["logits"], "config3 (ViT-L, 10 windows)")
 
 
+def test_config3_vitl_full_batch_across_videos():
+    """BASELINE config 3 at a size that fills a batch: ViT-L, 2 videos x 47 frames = 2 x 32 windows, scored through
+    runner.score_videos as ONE 64-window batch across the video boundary; all 64 against the unmodified reference."""
+    from simple_tad_b200.runner import SlidingWindowRunner
+    g = parity.golden("c3_vitl_2x47")
+    sd = synth.make_state_dict("vit_large_patch16_224", seed=3)
+    model = parity.build_classifier("vit_large_patch16_224", sd)
+    videos = [synth.make_video(47, seed=3 + v) for v in range(2)]
+    got = SlidingWindowRunner(model, batch_windows=64).score_videos(videos)
+    assert got.shape == (64, 2)
+    parity.check_logits(got, g["logits"], "config3 (ViT-L, 2 x 32 windows, one batch)")
+    per_video = torch.cat([model.forward_windows(v.to(DEV))[0] for v in videos])
+    parity.check_logits(per_video, g["logits"], "config3 (ViT-L, 2 x 32 windows, per video)")
+
+
 def test_config4_masked_encoder():
     """BASELINE config 4: ViT-B encoder, 90 % tube masking -> [B, 160, 768]; cosine >= 0.999 per token row."""
     g = parity.golden("c4_enc_vitb_b4")
@@ -430,6 +445,10 @@ def test_config5_batch_sweep_consistency():
     big = torch.cat([x, synth.make_clips(56, seed=50).to(DEV)])
     out = model(big)                                      # B = 64, the bench batch
     parity.check_logits(out[:8], ref, "config5 B=64 (first 8)")
+    # all 64 clips of the bench batch against the unmodified reference (fixture c5_vitb_b64; its first 8 = c5_vitb_b8)
+    g64 = parity.golden("c5_vitb_b64")
+    assert (g64["logits"][:8] == ref).all() or float(abs(g64["logits"][:8] - ref).max()) < 1e-4
+    parity.check_logits(out, g64["logits"], "config5 B=64 (all 64)")
 
 
 def test_modules_are_drop_in():
