@@ -108,15 +108,22 @@ struct Unit {
   bool split;
 };
 
-STAD_DEVICE Unit decode_unit(int u, int units_per_head, int H, int S) {
+// the part of a unit that depends only on its position t within the head (all the softmax warps and the MMA issuers
+// need; they step t incrementally instead of dividing at every unit boundary, which is on their critical path)
+STAD_DEVICE Unit unit_shape(int t, int S) {
   Unit w;
-  const int bh = u / units_per_head;
-  const int t = u - bh * units_per_head;
-  w.b = bh / H;
-  w.h = bh - w.b * H;
+  w.b = w.h = 0;
   w.q0 = t * 2 * BQ;
   w.slots = (w.q0 + BQ < S) ? 2 : 1;
   w.split = w.slots == 1 && S - w.q0 <= SPLIT_ROWS;
+  return w;
+}
+
+STAD_DEVICE Unit decode_unit(int u, int units_per_head, int H, int S) {
+  const int bh = u / units_per_head;
+  Unit w = unit_shape(u - bh * units_per_head, S);
+  w.b = bh / H;
+  w.h = bh - w.b * H;
   return w;
 }
 
@@ -160,6 +167,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int units_per_head = (n_q + 1) / 2;
   const int total_units = p.B * p.H * units_per_head;
   const int n_kv = (p.S + BKV - 1) / BKV;
+  // position within the head of this CTA's first unit, and of unit u + gridDim.x given that of unit u
+  const int t_first = static_cast<int>(blockIdx.x) % units_per_head;
+  const int t_step = static_cast<int>(gridDim.x) % units_per_head;
+  auto next_t = [&](int t) {
+    t += t_step;
+    return t >= units_per_head ? t - units_per_head : t;
+  };
   // The keys beyond the last multiple of 96 form a short ("ragged") tile.  It is processed FIRST (tile 0 of every
   // unit), the full tiles follow: the first tile of a unit is special anyway (it takes the exact row max that becomes
   // the lazy reference, with all its exps on the MUFU), and a separate ragged tile at the end costs nearly a full
@@ -181,7 +195,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&o_full[s], 1);
       mbar_init(&l_ready[s], BQ);
-      mbar_init(&o_free[s], 4);
+      mbar_init(&o_free[s], BQ);  // one arrive per epilogue thread
       mbar_init(&o_done[s], 1);
     }
     for (int s = 0; s < 4; ++s) {
@@ -276,127 +290,167 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // Both slots read the same K / V ring stages; a stage is released by two arrivals (one per slot; in a one-slot
       // unit the slot-0 warp commits twice).
       // The K/V tiles of all units of this slot are ONE stream t = 0, 1, 2, ...: tile t uses score buffer t & 1, and
-      // Q K_{t+2}^T is issued right behind P_t V_t whether or not tile t + 2 belongs to the same unit.  Two cursors
-      // walk the unit list: `qk` (two tiles ahead) and `pv`.
+      // Q K_{t+2}^T is issued right behind P_t V_t, also when tile t + 2 belongs to the NEXT unit (its first two score
+      // tiles are then complete when the softmax warps get there).
+      // This warp sits on the hand-over P_t stored -> P_t V_t -> Q K_{t+2}^T -> S_{t+2}, which has little slack (one
+      // more already-satisfied barrier test per tile costs 1 - 2 % of the kernel, measured): its per-tile path is kept
+      // short — ring positions and phases are stepped, not divided; no per-tile unit bookkeeping.
       const int slot = warp - kMmaWarp0;
 #ifdef STAD_ATT_TRACE
       int tr_n = 0;
 #endif
       constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, HD, 0, 1);   // P from TMEM (K-major), V MN-major (d contiguous)
       constexpr uint32_t idesc_qk = make_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major
+      const uint32_t idesc_qk_ragged = make_idesc_bf16(BQ, static_cast<uint32_t>(last_chunks * 32), 0, 0);
+      const int ksteps_ragged = last_chunks * 2;  // (no ragged tile: = BKV / 16)
+      const bool has_ragged = last_valid != BKV;
       const uint64_t desc_q_base = make_smem_desc_sw128(smem_u32(smem_q + slot * Q_BUFS * Q_BYTES), 16, 1024);
+      const uint64_t desc_k_base = make_smem_desc_sw128(smem_u32(smem_k), 16, 1024);
+      const uint64_t desc_v_base = make_smem_desc_sw128(smem_u32(smem_v), 0, 1024);
       const uint32_t tmem_slot_base = tmem_base + slot * SLOT_COLS;
       const uint32_t tmem_o = tmem_slot_base + O_COL;
-      struct Cursor {
-        int u;         // unit index (this CTA's units: blockIdx.x, + gridDim.x, ...)
-        int j;         // K/V tile within the unit
-        uint32_t t;    // tiles of this slot before (u, j): score buffer t & 1, its (t >> 1)-th use
-        uint32_t n;    // units of this slot before u (Q buffer n % Q_BUFS; phase of o_free)
-        uint32_t ring; // K (qk cursor) / V (pv cursor) tiles of the CTA before (u, j), skipped units included
-        bool solo;     // one-slot unit
-        bool gap;      // the cursor skipped at least one unit (one this slot sits out) on its way to u
-      };
-      // position the cursor on the next unit (from c.u on) this slot takes part in; false: no more units
-      auto seek = [&](Cursor& c) {
-        c.gap = false;
-        while (c.u < total_units) {
-          const Unit w = decode_unit(c.u, units_per_head, p.H, p.S);
-          if (slot < w.slots) {
-            c.solo = w.slots == 1;
-            return true;
-          }
-          c.ring += n_kv;  // one-slot unit: slot 1 sits it out but stays in step with the rings
-          c.u += gridDim.x;
-          c.gap = true;
+      uint64_t* const s_full_s = s_full + slot * 2;
+      uint64_t* const p_full_s = p_full + slot * 2;
+      uint64_t* const q_full_s = q_full + slot * Q_BUFS;
+      uint64_t* const q_free_s = q_free + slot * Q_BUFS;
+      // K ring position of the next Q K^T, V ring position of the next P V (stage, phase); tiles issued so far
+      uint32_t kst = 0, kph = 0, vst = 0, vph = 0;
+      uint32_t tq = 0, tp = 0;
+      // a unit this slot sits out advances a ring position by n_kv tiles
+      const uint32_t skip_st = static_cast<uint32_t>(n_kv) % KV_STAGES, skip_ph = (static_cast<uint32_t>(n_kv) / KV_STAGES) & 1u;
+      auto skip_unit = [&](uint32_t& st, uint32_t& ph) {
+        st += skip_st;
+        ph ^= skip_ph;
+        if (st >= KV_STAGES) {
+          st -= KV_STAGES;
+          ph ^= 1u;
         }
-        return false;
       };
-      auto advance = [&](Cursor& c) {
-        ++c.t;
-        ++c.ring;
-        if (++c.j < n_kv) return true;
-        c.j = 0;
-        ++c.n;
-        c.u += gridDim.x;
-        return seek(c);
-      };
-      // S = Q K_j^T of the qk cursor's tile into score buffer t & 1; releases the K stage (and Q after the unit's last tile)
-      auto issue_qk = [&](const Cursor& c) {
-        const uint32_t qb = c.n % Q_BUFS;
-        if (c.j == 0) mbar_wait(&q_full[slot * Q_BUFS + qb], (c.n / Q_BUFS) & 1);
-        const uint32_t kst = c.ring % KV_STAGES;
-        mbar_wait(&k_full[kst], (c.ring / KV_STAGES) & 1);
+      // S = Q K_j^T of unit number n (of this slot) into score buffer tq & 1; releases the K stage, and the Q tile
+      // after the unit's last tile
+      auto issue_qk = [&](uint32_t n, bool first, bool last, bool solo) {
+        const uint32_t qb = n % Q_BUFS;
+        if (first) mbar_wait(&q_full_s[qb], (n / Q_BUFS) & 1);
+        mbar_wait(&k_full[kst], kph);
         tc_fence_after();
-        const uint32_t buf = c.t & 1;
-        const bool last = c.j + 1 == n_kv;
+        const uint32_t buf = tq & 1;
         ATT_EV(2 + slot, 20);
         if (elect_one()) {
           const uint64_t desc_q = desc_q_base + static_cast<uint64_t>(qb * (Q_BYTES >> 4));
-          const uint64_t desc_k = make_smem_desc_sw128(smem_u32(smem_k + kst * KV_BYTES), 16, 1024);
+          const uint64_t desc_k = desc_k_base + static_cast<uint64_t>(kst * (KV_BYTES >> 4));
           const uint32_t tmem_s = tmem_slot_base + buf * BKV;
-          if (c.j != 0 || last_valid == BKV) {
+          const uint32_t idesc = (first && has_ragged) ? idesc_qk_ragged : idesc_qk;  // ragged tile: only its 32-key chunks
 #pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc_qk, k != 0);
-          } else {  // ragged tile: only the 32-key chunks that hold a valid key
-            const uint32_t idesc = make_idesc_bf16(BQ, static_cast<uint32_t>(last_chunks * 32), 0, 0);
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc, k != 0);
-          }
-          umma_commit(&s_full[slot * 2 + buf]);
-          if (last) umma_commit(&q_free[slot * Q_BUFS + qb]);
+          for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_s, desc_q + 2 * k, desc_k + 2 * k, idesc, k != 0);
+          umma_commit(&s_full_s[buf]);
+          if (last) umma_commit(&q_free_s[qb]);
           umma_commit(&k_free[kst]);
-          if (c.solo) umma_commit(&k_free[kst]);
+          if (solo) umma_commit(&k_free[kst]);
         }
         __syncwarp();
         ATT_EV(2 + slot, 21);
+        ++tq;
+        if (++kst == KV_STAGES) {
+          kst = 0;
+          kph ^= 1u;
+        }
       };
-      // O (+)= P_j V_j of the pv cursor's tile.  V tile: one 128-byte row per key -> MN-major B operand; 16 keys =
+      // O (+)= P_j V_j of unit number n.  V tile: one 128-byte row per key -> MN-major B operand; 16 keys =
       // 2 x 1024 B per MMA.
-      auto issue_pv = [&](const Cursor& c) {
-        const uint32_t vst = c.ring % KV_STAGES;
-        mbar_wait(&v_full[vst], (c.ring / KV_STAGES) & 1);
-        if (c.j == 0 && c.n > 0) mbar_wait(&o_free[slot], (c.n - 1) & 1);  // epilogue has read the previous unit's O
-        const uint32_t buf = c.t & 1;
+      auto issue_pv = [&](uint32_t n, bool first, bool last, bool solo) {
+        mbar_wait(&v_full[vst], vph);
+        if (first && n > 0) mbar_wait(&o_free[slot], (n - 1) & 1);  // epilogue has read the previous unit's O
+        // The previous P V of this slot, issued a tile ago, is complete.  Observing its o_full phase here, every tile
+        // and BEFORE the wait for P, means the barrier never runs a phase ahead of an observer: the parity waits of
+        // the softmax warps' slow path, its only other waiters and rare, cannot alias, and compute-sanitizer's
+        // synccheck (which rejects a barrier that completes phase after phase unobserved) stays clean.
+        if (tp > 0) mbar_wait(&o_full[slot], (tp - 1) & 1);
+        const uint32_t buf = tp & 1;
         ATT_EV(2 + slot, 22);
-        mbar_wait(&p_full[slot * 2 + buf], (c.t >> 1) & 1);
+        mbar_wait(&p_full_s[buf], (tp >> 1) & 1);
         tc_fence_after();
         ATT_EV(2 + slot, 23);
-        const int ksteps = (c.j == 0) ? last_chunks * 2 : BKV / 16;  // (no ragged tile: last_chunks * 2 = BKV / 16)
         if (elect_one()) {
-          const uint64_t desc_v = make_smem_desc_sw128(smem_u32(smem_v + vst * KV_BYTES), 0, 1024);
+          const uint64_t desc_v = desc_v_base + static_cast<uint64_t>(vst * (KV_BYTES >> 4));
           const uint32_t tmem_p = tmem_slot_base + buf * BKV;
-          if (ksteps == BKV / 16) {
+          if (!first) {
 #pragma unroll
-            for (int k = 0; k < BKV / 16; ++k)
-              umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, (c.j != 0 || k != 0) ? 1u : 0u);
-          } else {
-            for (int k = 0; k < ksteps; ++k)
-              umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, (c.j != 0 || k != 0) ? 1u : 0u);
+            for (int k = 0; k < BKV / 16; ++k) umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, 1u);
+          } else {  // first tile of the unit: starts the accumulation; the ragged tile if there is one
+            for (int k = 0; k < ksteps_ragged; ++k)
+              umma_ts(tmem_o, tmem_p + k * 8, desc_v + (k * 2048 >> 4), idesc_pv, k != 0 ? 1u : 0u);
           }
           umma_commit(&o_full[slot]);
-          if (c.j + 1 == n_kv) umma_commit(&o_done[slot]);
+          if (last) umma_commit(&o_done[slot]);
           umma_commit(&v_free[vst]);
-          if (c.solo) umma_commit(&v_free[vst]);
+          if (solo) umma_commit(&v_free[vst]);
         }
         __syncwarp();
         ATT_EV(2 + slot, 24);
+        ++tp;
+        if (++vst == KV_STAGES) {
+          vst = 0;
+          vph ^= 1u;
+        }
       };
 
-      Cursor qk = {static_cast<int>(blockIdx.x), 0, 0u, 0u, 0u, false, false};
-      Cursor pv = qk;
-      bool more_qk = seek(qk);
-      bool more_pv = seek(pv);
-      while (more_pv) {
-        // Up to two score tiles ahead of the P V stream.  NOT across a unit this slot sits out: the K tiles of that
-        // unit come first in the ring and are loaded only as V stages become free, and the V stages of this slot's
-        // current unit are released by P V this warp would be holding back while it waits for the K tile after the
-        // gap (deadlock).  Behind a gap the slot finishes its unit first, as it would without look-ahead.
-        while (more_qk && qk.t - pv.t < 2 && (!qk.gap || qk.u == pv.u)) {
-          issue_qk(qk);
-          more_qk = advance(qk);
+      // Unit list of this CTA: blockIdx.x, + gridDim.x, ...; `ut` = position within the head.
+      int u = blockIdx.x, ut = t_first;
+      // moves (u, ut) to the first unit from (u, ut) on that this slot takes part in; counts the units it skips
+      auto seek = [&](int& uu, int& uut, int& skipped, bool& solo) {
+        skipped = 0;
+        while (uu < total_units) {
+          const Unit w = unit_shape(uut, p.S);
+          if (slot < w.slots) {
+            solo = w.slots == 1;
+            return true;
+          }
+          ++skipped;
+          uu += gridDim.x;
+          uut = next_t(uut);
         }
-        issue_pv(pv);
-        more_pv = advance(pv);
+        return false;
+      };
+      int skipped = 0;
+      bool solo = false;
+      bool have = seek(u, ut, skipped, solo);
+      for (int i = 0; i < skipped; ++i) {
+        skip_unit(kst, kph);
+        skip_unit(vst, vph);
+      }
+      int pre = 0;      // Q K^T of the current unit already issued (by the look-ahead from the unit before)
+      uint32_t n = 0;   // number of this unit among the units of this slot
+      while (have) {
+        // the next unit of this slot.  Look-ahead NOT across units this slot sits out: their K tiles come first in the
+        // ring and are loaded only as V stages become free, and the V stages of the current unit are released by P V
+        // this warp would be holding back while it waits for the K tile behind the gap (deadlock).  Behind a gap the
+        // slot finishes its unit first, as it would without look-ahead.
+        int u2 = u + gridDim.x, ut2 = next_t(ut), skipped2 = 0;
+        bool solo2 = false;
+        const bool have2 = seek(u2, ut2, skipped2, solo2);
+        const bool look = have2 && skipped2 == 0;
+        for (; pre < 2 && pre < n_kv; ++pre) issue_qk(n, pre == 0, pre + 1 == n_kv, solo);
+        int pre2 = 0;
+        for (int j = 0; j < n_kv; ++j) {
+          issue_pv(n, j == 0, j + 1 == n_kv, solo);
+          const int jq = j + 2;
+          if (jq < n_kv) {
+            issue_qk(n, false, jq + 1 == n_kv, solo);
+          } else if (look && jq - n_kv == pre2) {  // (false with one tile per unit: the stream index is two units on)
+            issue_qk(n + 1, pre2 == 0, pre2 + 1 == n_kv, solo2);
+            ++pre2;
+          }
+        }
+        for (int i = 0; i < skipped2; ++i) {  // (look-ahead implies skipped2 == 0)
+          skip_unit(kst, kph);
+          skip_unit(vst, vph);
+        }
+        pre = pre2;
+        u = u2;
+        ut = ut2;
+        solo = solo2;
+        have = have2;
+        ++n;
       }
     }
 #ifdef STAD_ATT_TRACE
@@ -462,8 +516,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tmem_ld_wait16(ov);
             if (q == 3) {  // O is in registers: the next unit's first P V may overwrite it
               tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&o_free[slot]);
+              mbar_arrive(&o_free[slot]);
             }
             // a part that never saw a key (weight 0) holds whatever its all-zero P rows produced: exactly 0
 #pragma unroll
@@ -506,8 +559,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
           if (q == 1) {  // O is in registers: the next unit's first P V may overwrite it
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&o_free[slot]);
+            mbar_arrive(&o_free[slot]);
             ATT_E(42);
           }
           if (warp_valid && row < p.S) {
@@ -541,10 +593,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // End of a unit: row sum (and, key-split units, the reference max) to the epilogue warps.  The scores of the next
     // unit are computed ahead of time (see the MMA issuers), so with few K/V tiles per unit these warps can finish
     // unit n before the epilogue warps have taken unit n - 1: wait until they have (o_free: O and the row sums read).
-    // (With three or more tiles per unit the wait is implied: S of the unit's last tile exists only after the issuer
-    // has started the unit's first P V, for which it waited on the same o_free phase itself.)
+    // (With three or more tiles per unit the phase is always complete by now: S of the unit's last tile exists only
+    // after the issuer has started the unit's first P V, for which it waited on the same o_free phase itself.)
     auto hand_over = [&](float l, float m, bool with_max) {
-      if (un > 0 && n_kv < 3) mbar_wait(&o_free[slot], (un - 1) & 1);
+      if (un > 0) mbar_wait(&o_free[slot], (un - 1) & 1);
       lsum_smem[slot * BQ + r] = l;
       if (with_max) lsum_smem[2 * BQ + r] = m;
       mbar_arrive(&l_ready[slot]);
@@ -574,8 +626,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_arrive_a(p_bar);
     };
 
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const Unit w = decode_unit(u, units_per_head, p.H, p.S);
+    for (int u = blockIdx.x, ut = t_first; u < total_units; u += gridDim.x, ut = next_t(ut)) {
+      const Unit w = unit_shape(ut, p.S);
       if (slot >= w.slots) continue;
       if (w.split) {
         // ---- key-split tail unit (slot 0 only): lane i of EVERY quarter holds query q0 + i; the warp of quarter k < 3
@@ -643,13 +695,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       uint32_t sp = slot_addr + buf * BKV;
       uint32_t s_bar = s_full_a + buf * 8, p_bar = p_full_a + buf * 8;
       uint32_t ph = (g >> 1) & 1;
+      // All four warps of slot 1 wait at this ONE bar.sync, whether their rows are valid or not (slot 0 of a two-slot
+      // unit has no invalid rows, and arrives from the first tile below).
+      if (stagger && slot == 1) named_bar_sync(1, 2 * BQ);
       if (row0 + quarter * 32 >= p.S) {
         // rows beyond S (warp-uniform): nothing to compute (their P / O rows are never stored); keep the pipeline
         // moving.  (The previous phase of p_full[buf] is complete: Q K_j^T was issued after P_{j-2} V_{j-2}.)
-        if (stagger) {
-          if (slot == 1) named_bar_sync(1, 2 * BQ);
-          else asm volatile("bar.arrive 1, %0;" ::"n"(2 * BQ) : "memory");
-        }
         for (int j = 0; j < n_kv; ++j, ++g) {
           mbar_wait_a(s_bar, ph);
           mbar_arrive_a(p_bar);
@@ -668,7 +719,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // instructions and a constant-bank load on the critical path of the tile).
       int n_tiles = n_kv;
       asm volatile("" : "+r"(n_tiles));
-      if (stagger && slot == 1) named_bar_sync(1, 2 * BQ);
 
       for (int j = 0; j < n_tiles; ++j, ++g, ph ^= buf, buf ^= 1, sp ^= BKV, s_bar ^= 8, p_bar ^= 8) {
         ATT_T(7);

@@ -62,10 +62,34 @@ STAD_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking phase test (mbarrier.try_wait may suspend the thread for a system-dependent time when the phase is
+// still pending)
+STAD_DEVICE bool mbar_test_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 STAD_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_test_wait_a(smem_u32(bar), parity)) return;  // usual case on the hot paths: the phase completed long ago
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > STAD_WAIT_SPIN_LIMIT) __trap();  // surfaces as cudaErrorLaunchFailure instead of a hung device
+  }
+}
+
+// plain try_wait loop (no test_wait first)
+STAD_DEVICE void mbar_wait_try(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > STAD_WAIT_SPIN_LIMIT) __trap();
   }
 }
 
@@ -87,6 +111,7 @@ STAD_DEVICE bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 STAD_DEVICE void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  if (mbar_test_wait_a(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait_a(bar, parity)) {
     if (++spins > STAD_WAIT_SPIN_LIMIT) __trap();
