@@ -74,11 +74,18 @@ int make_geom(const stad_dims* d, const stad_input* in, int B, PatchGeom* pg) {
   return STAD_OK;
 }
 
-// Up to this many rows the LN-folded GEMMs finish the LayerNorm statistics themselves (see run_blocks).  Measured
-// (profiles/r1c_fold_threshold_ab.txt): 34.4 k clips/s on the 16000-row DAPT batch at 8192 against 33.8 k / 34.0 k at
-// 32768 / 65536 — larger batches keep the 5 us finalize kernel.
+// When the LN-folded GEMMs finish the LayerNorm statistics themselves instead of a stats_finalize launch (see
+// run_blocks).  With at most kGemmMaxFoldParts partials per row they are prefetched a tile ahead (registers), off the
+// head of the epilogue: folding then pays up to a few ten thousand rows (DAPT, 16000 rows: 3.08 -> 2.89 ms per 100
+// clips); at the 100352 rows of the headline batch the 24 extra-long epilogues still cost more than the 24 finalize
+// launches they replace (same box, profiles/r2b_fold_ab.txt: 2742-2764 vs 2770-2774 clips/s).  With more partials
+// (narrow column tiles, i.e. small batches) the loads stay at the head of each tile: up to 8192 rows
+// (profiles/r1c_fold_threshold_ab.txt).
 constexpr int kFoldStatsMaxRows = 8192;
-int fold_stats_max_rows() { return kFoldStatsMaxRows; }
+constexpr int kFoldStatsMaxRowsPrefetched = 32768;
+bool fold_stats_for(int M, int parts) {
+  return M <= (parts <= kGemmMaxFoldParts ? kFoldStatsMaxRowsPrefetched : kFoldStatsMaxRows);
+}
 
 size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
@@ -188,7 +195,6 @@ int run_blocks(const stad_block* blocks, const stad_dims* d, float eps, float at
   const int M = B * n_tok;
   const int D = d->dim;
   const int parts_resid = gemm_stat_parts(M, D, false, nullptr);
-  const bool fold_stats = M <= fold_stats_max_rows();
   int parts = parts_in;
   int rc;
   for (int l = 0; l < d->depth; ++l) {
@@ -203,7 +209,7 @@ int run_blocks(const stad_block* blocks, const stad_dims* d, float eps, float at
     GemmArgs q;
     q.a = ws.x; q.w = static_cast<const bf16*>(blk.w_qkv); q.M = M; q.N = 3 * D; q.K = D;
     q.epi = EPI_LN; q.bias = blk.b_qkv; q.colsum = blk.cs_qkv; q.out = ws.qkv; q.ln_eps = eps;
-    if (parts > 0 && fold_stats) {
+    if (parts > 0 && fold_stats_for(M, parts)) {
       q.stat_parts = ws.parts; q.n_stat_parts = parts;
     } else {
       if (parts > 0) {
@@ -223,7 +229,7 @@ int run_blocks(const stad_block* blocks, const stad_dims* d, float eps, float at
     GemmArgs f1;
     f1.a = ws.x; f1.w = static_cast<const bf16*>(blk.w_fc1); f1.M = M; f1.N = d->hidden; f1.K = D;
     f1.epi = EPI_LN | EPI_GELU; f1.bias = blk.b_fc1; f1.colsum = blk.cs_fc1; f1.out = ws.hidden; f1.ln_eps = eps;
-    if (fold_stats) {
+    if (fold_stats_for(M, parts)) {
       f1.stat_parts = ws.parts; f1.n_stat_parts = parts;
     } else {
       if ((rc = launch_stats_finalize(ws.parts, parts, ws.stats, M, D, eps, stream))) return rc;

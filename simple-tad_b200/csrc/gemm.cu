@@ -27,6 +27,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
+constexpr int kMaxFoldParts = kGemmMaxFoldParts;  // see kernels.h
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kSubCols = 32;                      // columns per epilogue sub-tile = one tcgen05.ld.x32 = one TMA store
 constexpr int kSubTileBytes = BM * kSubCols * 2;  // 8 KB: 128 rows x 64 B, SWIZZLE_64B
@@ -337,6 +338,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (elect_one()) prepare_buffer(0);
       __syncwarp();
     }
+    // EPI_LN with stat_parts: the partial (sum, sumsq) of this thread's row are fetched one tile AHEAD (registers), so
+    // their L2 latency is hidden behind the previous tile's epilogue instead of sitting at the head of every tile's
+    // (the dynamic loop of dependent loads it replaces made folding a loss beyond ~8 k rows; now every LayerNorm-folded
+    // GEMM finishes its own statistics and the stats_finalize launches are gone from the model paths).
+    float2 pre_parts[kMaxFoldParts];
+    auto fetch_parts = [&](int tile) {
+      if constexpr (EPI & EPI_LN) {
+        if (p.stat_parts != nullptr && p.n_stat_parts <= kMaxFoldParts && tile < num_tiles) {
+          const TileRows t = tile_rows<kPatch>(p, m_tile_of(tile));
+          const bool ok = r < t.valid_rows;
+          const float2* src = p.stat_parts + (t.row0 + r);
+#pragma unroll
+          for (int i = 0; i < kMaxFoldParts; ++i)
+            pre_parts[i] = (ok && i < p.n_stat_parts) ? __ldg(src + static_cast<size_t>(i) * p.M) : make_float2(0.f, 0.f);
+        }
+      }
+    };
+    fetch_parts(worker);
     int local = 0;
     for (int tile = worker; tile < num_tiles; tile += n_workers, ++local) {
       const int m_tile = m_tile_of(tile);
@@ -352,12 +371,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (row_ok) {
           if (p.stat_parts != nullptr) {
             // LayerNorm statistics straight from the partial sums the producing GEMM emitted: the same index-order
-            // sum and the same arithmetic as stats_finalize_kernel (bit-identical), without that launch
+            // sum and the same arithmetic as stats_finalize_kernel (bit-identical; absent parts add 0), without that
+            // launch
             float s1 = 0.f, s2 = 0.f;
-            for (int i = 0; i < p.n_stat_parts; ++i) {
-              const float2 v = __ldg(&p.stat_parts[static_cast<size_t>(i) * p.M + row]);
-              s1 += v.x;
-              s2 += v.y;
+            if (p.n_stat_parts <= kMaxFoldParts) {
+#pragma unroll
+              for (int i = 0; i < kMaxFoldParts; ++i) {
+                s1 += pre_parts[i].x;
+                s2 += pre_parts[i].y;
+              }
+            } else {  // many narrow column tiles (small batches): few tiles per CTA, nothing to hide the loads behind
+              for (int i = 0; i < p.n_stat_parts; ++i) {
+                const float2 v = __ldg(&p.stat_parts[static_cast<size_t>(i) * p.M + row]);
+                s1 += v.x;
+                s2 += v.y;
+              }
             }
             mean = s1 * p.ln_inv_d;
             const float var = fmaxf(fmaf(-mean, mean, s2 * p.ln_inv_d), 0.f);
@@ -368,6 +396,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             rstd = st.y;
           }
         }
+        fetch_parts(tile + n_workers);
       }
       float st_sum = 0.f, st_sq = 0.f;  // EPI_STATS: running (sum, sumsq) of this thread's part of the row
       const float* pos_row = nullptr;

@@ -24,6 +24,8 @@ enum : int { EPI_LN = 1, EPI_GELU = 2, EPI_RESID = 4, EPI_POS = 8, EPI_STATS = 1
 // of the bf16 values it stored; launch_stats_finalize adds a row's partials in index order (deterministic, no atomics)
 // and writes (mean, rstd) for the following LN-folded GEMM (nn.LayerNorm statistics, modeling_finetune.py:143/149).
 constexpr int kMaxStatParts = 32;  // 2 * N / 64 at the narrowest column tile, N <= 1024
+// up to this many partials per row an EPI_LN GEMM prefetches them a tile ahead (registers); see gemm.cu
+constexpr int kGemmMaxFoldParts = 8;
 
 struct GemmArgs {
   const bf16* a = nullptr;  // [M, K] (plain) or the bf16 plane tensor (patch mode)
