@@ -187,6 +187,40 @@ def check_gemm_stats(M=3136, D=768, N2=3072, K1=768, seed=0):
 
 
 # ------------------------------------------------------------------------------------------------------- attention
+def check_attention_outliers(B=2, H=2, S=1568, seed=0, gains=(8.0, 16.0)):
+    """Adversarial scores for the lazy reference max: the reference of a row is the exact max of the unit's FIRST key tile
+    (the ragged tail of the sequence, 32 keys at S = 1568).  Every 5th query row gets keys planted in later tiles that
+    score 90+ and 180+ octaves above everything before them (k_j = gain * q_row), in increasing order, so that the row
+    sum guard trips once or twice in the same unit (slow path: exact max of the tile, O and row sum rescaled, tile
+    redone); every 7th row gets its dominant key INSIDE the first tile.  The fp32 reference puts ~all weight on the last
+    planted key."""
+    qkv = _bf16(B, S, 3, H, 64, seed=seed + 31, scale=1.0)
+    g = torch.Generator().manual_seed(seed + 32)
+    n_tiles = (S + 95) // 96
+    for b in range(B):
+        for h in range(H):
+            for r in range(0, S, 5):
+                # two planted keys at increasing positions in DIFFERENT key tiles (tile order of the kernel: ragged tail
+                # first, then keys 0, 96, 192, ...), never in the ragged tail itself
+                full = (S // 96) * 96
+                if full < 192:
+                    continue
+                j1 = int(torch.randint(0, full // 2, (1,), generator=g))
+                j2 = int(torch.randint(full // 2, full, (1,), generator=g))
+                qkv[b, j1, 1, h] = (gains[0] * qkv[b, r, 0, h].float()).to(torch.bfloat16)
+                qkv[b, j2, 1, h] = (gains[1] * qkv[b, r, 0, h].float()).to(torch.bfloat16)
+            if S % 96:
+                for r in range(3, S, 7):
+                    j0 = (S // 96) * 96 + int(torch.randint(0, S % 96, (1,), generator=g))
+                    qkv[b, j0, 1, h] = (4.0 * qkv[b, r, 0, h].float()).to(torch.bfloat16)
+    out = L.attention(qkv)
+    torch.cuda.synchronize()
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3).float() for i in range(3))  # [B,H,S,64]
+    att = (q * 64 ** -0.5) @ k.transpose(-1, -2)
+    ref = (att.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B, S, H * 64)
+    return _stats(out, ref, f"attention_outliers[B{B},H{H},S{S}]", 2e-2, 2e-2)
+
+
 def check_attention(B=2, H=3, S=1568, peaky=1.0, seed=0):
     qkv = _bf16(B, S, 3, H, 64, seed=seed + 21, scale=1.0)
     if peaky != 1.0:
@@ -381,6 +415,11 @@ CHECKS = {
     "gemm_ln_gelu": lambda: [check_gemm(3136, 3072, 768, "ln_gelu"), check_gemm(1568, 4096, 1024, "ln_gelu")],
     "gemm_stats": lambda: [check_gemm_stats(3136, 768, 3072, 768), check_gemm_stats(1568, 384, 1152, 1536, seed=3),
                            check_gemm_stats(200, 1024, 1024, 4096, seed=5)],
+    # planted keys far above the lazy reference (slow path: guard trip, rescale, redo), also in multi-unit CTAs, a
+    # class-token length and a key-split tail; S = 160 / 392: two / five tiles per unit
+    "attention_outliers": lambda: [check_attention_outliers(2, 2, 1568), check_attention_outliers(30, 6, 392, seed=2),
+                                   check_attention_outliers(1, 3, 1569, seed=3), check_attention_outliers(80, 4, 288, seed=4),
+                                   check_attention_outliers(3, 12, 1568, seed=5, gains=(30.0, 200.0))],
     "attention_small": lambda: check_attention(1, 1, 128),
     "attention_tail": lambda: [check_attention(1, 2, 160), check_attention(2, 1, 392)],
     "attention": lambda: [check_attention(2, 3, 1568), check_attention(1, 12, 1568, peaky=6.0)],

@@ -21,7 +21,8 @@ GROUPS = {
                      kc.check_gemm(9472, 1024, 768, "ln_gelu", seed=8), kc.check_gemm_stats(9472, 768, 512, 768, seed=9)],
     "attention": lambda: [kc.check_attention(1, 2, 288, seed=1), kc.check_attention(1, 1, 160, seed=2),
                           kc.check_attention(2, 1, 100, seed=3), kc.check_attention(1, 1, 417, peaky=4.0, seed=4),
-                          kc.check_attention(40, 4, 160, seed=5)],
+                          kc.check_attention(40, 4, 160, seed=5), kc.check_attention_outliers(1, 2, 288, seed=6),
+                          kc.check_attention_outliers(20, 4, 392, seed=7)],
     "rows": lambda: [kc.check_pool_head(3, 160, 384), kc.check_layernorm(100, 768), kc.check_row_stats(100, 384),
                      kc.check_normalize_u8(2, 64, 64), kc.check_decoder_assemble(2, 196, 20, 192, seed=50)],
 }
