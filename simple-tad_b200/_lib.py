@@ -145,6 +145,11 @@ def init(device=None):
         with torch.cuda.device(idx):
             check(load().stad_init(idx), "stad_init")
         _inited_devices.add(idx)
+    # the library launches on the CURRENT device and the wrappers pass torch's current stream of that device: a tensor
+    # on another GPU of the same process would be read through a stream of the wrong device, so refuse it here
+    if device is not None and idx != torch.cuda.current_device():
+        raise RuntimeError(f"simple-tad_b200: tensor lives on cuda:{idx} but the current device is "
+                           f"cuda:{torch.cuda.current_device()}; wrap the call in torch.cuda.device({idx})")
     return idx
 
 

@@ -12,7 +12,7 @@ namespace stad {
 
 namespace {
 thread_local char g_err[512] = "";
-int g_sm_count = 0;
+int g_sm_count[64] = {};
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 std::once_flag g_encode_once;
 
@@ -110,14 +110,18 @@ const char* last_error() { return g_err; }
 
 bool pdl_enabled() { return true; }  // programmatic dependent launch on every GEMM / attention / finalize launch
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs through the C ABI)
 int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = g_sm_count[dev];
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    g_sm_count[dev] = n;
   }
-  return g_sm_count;
+  return n;
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
