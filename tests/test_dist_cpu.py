@@ -173,6 +173,19 @@ def test_score_videos_windows_follow_the_sequencer_world_size_2_gloo(tmp_path, s
         assert got.shape == want.shape and torch.equal(got, want), f"rank {r}: window table differs from the sequencer's"
 
 
+@pytest.mark.parametrize("world", [4, 8])
+def test_score_videos_config3_geometry_world_size_4_and_8_gloo(tmp_path, world):
+    """BASELINE config 3 geometry (8 videos x 100 frames = 680 windows) sharded over 4 and 8 ranks: at 8 ranks every
+    shard is 85 windows = one video's worth but NOT aligned to the videos' window ranges once padding enters; every rank
+    must end up with the identical, complete [680, 2] table."""
+    lengths = [100] * 8
+    mp.spawn(_runner_worker, args=(world, _free_port(), str(tmp_path), lengths, 1, 1), nprocs=world, join=True)
+    want = torch.tensor([(1000.0 * v + w + 15, 1000.0 * v + w) for v in range(8) for w in range(85)])
+    for r in range(world):
+        got = torch.load(os.path.join(str(tmp_path), f"s{r}.pt"))
+        assert got.shape == want.shape and torch.equal(got, want), f"rank {r} of {world}: window table differs"
+
+
 def test_score_videos_runs_full_batches_across_video_boundaries():
     """BASELINE config 3 shape (8 videos x 100 frames = 8 x 85 windows): the shard of a rank is scored in FULL batches of
     `batch_windows` windows wherever the video boundaries fall (the reference's DataLoader batches windows across
