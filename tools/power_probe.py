@@ -63,13 +63,16 @@ def probe(name, fn, flops, handle, seconds):
 
 def main():
     seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 2.5
-    quick = len(sys.argv) > 2 and sys.argv[2] == "quick"  # no cuBLAS comparators
+    quick = len(sys.argv) > 2 and sys.argv[2] in ("quick", "attention")  # no cuBLAS comparators
+    only_attention = len(sys.argv) > 2 and sys.argv[2] == "attention"
     pynvml.nvmlInit()
     handle = pynvml.nvmlDeviceGetHandleByIndex(0)
     B, S, D, H = 64, 1568, 768, 12
     M = B * S
     qkv = torch.randn(B, S, 3, H, 64, device="cuda").to(torch.bfloat16)
     probe("attention 64x12x1568", lambda: L.attention(qkv), 4.0 * B * H * S * S * 64, handle, seconds)
+    if only_attention:
+        return
     a = torch.randn(M, D, device="cuda").to(torch.bfloat16)
     ah = torch.randn(M, 4 * D, device="cuda").to(torch.bfloat16)
     res = torch.randn(M, D, device="cuda").to(torch.bfloat16)
