@@ -150,8 +150,22 @@ stats_finalize_kernel(const float2* __restrict__ parts, int n_parts, float2* __r
   pdl_wait();  // launched as a programmatic dependent of the GEMM that wrote `parts`
   if (row >= M) return;
   float s1 = 0.f, s2 = 0.f;
-  for (int i = 0; i < n_parts; ++i) {
-    const float2 v = __ldg(&parts[static_cast<size_t>(i) * M + row]);
+  // eight independent loads in flight per thread (one dependent load per iteration runs at a third of the copy rate:
+  // 9 us for the 19 MB of a 100352-row ViT-B step, 24 times per step); the adds stay in index order
+  const float2* src = parts + row;
+  int i = 0;
+  for (; i + 8 <= n_parts; i += 8) {
+    float2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(&src[static_cast<size_t>(i + k) * M]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s1 += v[k].x;
+      s2 += v[k].y;
+    }
+  }
+  for (; i < n_parts; ++i) {
+    const float2 v = __ldg(&src[static_cast<size_t>(i) * M]);
     s1 += v.x;
     s2 += v.y;
   }

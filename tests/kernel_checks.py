@@ -383,7 +383,75 @@ def check_gemm_pair():
     return out
 
 
+# ------------------------------------------------------------------------------- full-size, size-independent properties
+def check_gemm_integer_exact(M=64 * 1568, N=2304, K=768, mode="bias", seed=0):
+    """The bench step's GEMM shapes with small-integer operands: every product and every partial sum is an integer
+    below 2^24 and every result an integer of magnitude <= 256, so fp32 accumulation in ANY order and the bf16 store are
+    exact — the kernel must reproduce the fp32 matmul bit for bit on all M x N outputs (a dropped k-block, a tile
+    written twice or a mis-addressed row in any of the ~3600 tiles shows as an integer error)."""
+    g = torch.Generator(device=DEV).manual_seed(seed + 500)
+
+    def sparse_pm1(rows, cols):  # entries in {-1, 0, 1}, three quarters of them zero
+        t = torch.randint(-1, 2, (rows, cols), generator=g, device=DEV, dtype=torch.int8)
+        keep = torch.rand(rows, cols, generator=g, device=DEV) < 0.25
+        return (t * keep).to(torch.bfloat16)
+
+    a, w = sparse_pm1(M, K), sparse_pm1(N, K)
+    bias = torch.randint(-3, 4, (N,), generator=g, device=DEV).float()
+    res = torch.randint(-8, 9, (M, N), generator=g, device=DEV).to(torch.bfloat16) if mode == "resid" else None
+    out = L.gemm_bias_residual(a, w, bias, res)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for r0 in range(0, M, 16384):  # fp32 reference by row blocks (the full product would be another M x N fp32 buffer)
+        ref = a[r0:r0 + 16384].float() @ w.float().t() + bias
+        if res is not None:
+            ref = ref + res[r0:r0 + 16384].float()
+        assert float(ref.abs().max()) <= 256.0
+        d = (out[r0:r0 + 16384].float() - ref).abs().max()
+        worst = max(worst, float(d))
+    assert worst == 0.0, f"gemm.{mode}[{M}x{N}x{K}] integer operands: max |diff| = {worst} (must be exact)"
+    return {"name": f"gemm_integer_exact.{mode}[{M}x{N}x{K}]", "max_abs": worst}
+
+
+def check_attention_full_size_properties(B=64, H=12, S=1568, seed=0):
+    """The bench step's attention launch (5376 units on 148 CTAs), through properties that need no S x S reference:
+    (1) rows of softmax sum to one: with V constant along the keys the output equals that constant, whatever Q and K;
+    (2) a joint permutation of the keys of K and V leaves the output unchanged up to rounding (different tiling of the
+        same sum);
+    (3) sampled (clip, head) pairs against the fp32 softmax(Q K^T) V."""
+    qkv = _bf16(B, S, 3, H, 64, seed=seed + 600, scale=1.0)
+    out = L.attention(qkv)
+    # (1)
+    const = _bf16(B, 1, H, 64, seed=seed + 601)
+    qkv_c = qkv.clone()
+    qkv_c[:, :, 2] = const
+    out_c = L.attention(qkv_c)
+    torch.cuda.synchronize()
+    want = const.float().reshape(B, 1, H * 64).expand(B, S, H * 64)
+    s1 = _stats(out_c, want, f"attention.const_v[B{B},H{H},S{S}]", 1e-3, 1e-2)
+    # (2)
+    perm = torch.randperm(S, generator=torch.Generator().manual_seed(seed + 602)).to(DEV)
+    qkv_p = qkv.clone()
+    qkv_p[:, :, 1:] = qkv[:, perm, 1:]
+    out_p = L.attention(qkv_p)
+    torch.cuda.synchronize()
+    s2 = _stats(out_p, out, f"attention.key_permutation[B{B},H{H},S{S}]", 1e-2, 2e-2)
+    # (3)
+    g = torch.Generator().manual_seed(seed + 603)
+    for _ in range(6):
+        b, h = int(torch.randint(0, B, (1,), generator=g)), int(torch.randint(0, H, (1,), generator=g))
+        q, k, v = (qkv[b, :, i, h].float() for i in range(3))
+        ref = ((q * 64 ** -0.5) @ k.t()).softmax(-1) @ v
+        _stats(out[b, :, h * 64:(h + 1) * 64], ref, f"attention.sample[b{b},h{h}]", 2e-2, 2e-2)
+    return [s1, s2]
+
+
+
 CHECKS = {
+    "gemm_integer_exact": lambda: [check_gemm_integer_exact(64 * 1568, 2304, 768, "bias"),
+                                   check_gemm_integer_exact(64 * 1568, 768, 3072, "resid", seed=1),
+                                   check_gemm_integer_exact(128 * 1568, 384, 384, "resid", seed=2)],
+    "attention_full_size": check_attention_full_size_properties,
     "rows_norm_head": lambda: [check_rows_norm_head(3, 1568, 768, 2, "all"), check_rows_norm_head(5, 1569, 384, 2, "cls"),
                                check_rows_norm_head(2, 100, 1024, 40, "all", seed=61),
                                check_rows_norm_head(4, 7, 384, 400, "cls", seed=62)],
