@@ -28,6 +28,38 @@ GROUPS = {
 }
 
 
+def _model_forward():
+    """Whole small forward (ViT-S width, 2 blocks, 2 clips = 3136 rows): the path on which the LayerNorm-folded GEMMs finish
+    the statistics themselves from the prefetched partial sums (M <= 32768), the patch-embed GEMM with its 5-D tensor map,
+    pool + head; plus the masked encoder (visible-token gather).  Two runs must agree bit for bit."""
+    from functools import partial
+    import synth_data as synth
+    from simple_tad_b200 import modeling_finetune as mf, modeling_pretrain as mp
+    arch = "vit_small_d2"
+    D, depth, heads = synth.ARCHS[arch]
+    model = mf.VisionTransformer(patch_size=16, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
+                                 norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=2, all_frames=16,
+                                 tubelet_size=2, init_scale=1.0, final_reduction="fc_norm")
+    model.load_state_dict(synth.make_state_dict(arch, seed=7))
+    model = model.cuda().eval()
+    x = synth.make_clips(2, seed=7).cuda()
+    a = model(x)
+    b = model(x)
+    torch.cuda.synchronize()
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+    enc = mp.PretrainVisionTransformerEncoder(embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
+                                              norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), init_values=0.)
+    enc.load_state_dict(synth.make_state_dict(arch, seed=8, encoder=True))
+    enc = enc.cuda().eval()
+    y = enc(x, synth.tube_mask(2, 0.9, seed=8).cuda())
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    return [a, y]
+
+
+GROUPS["model"] = _model_forward
+
+
 def main():
     names = sys.argv[1:] or list(GROUPS)
     for n in names:
