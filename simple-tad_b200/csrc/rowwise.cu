@@ -150,24 +150,22 @@ stats_finalize_kernel(const float2* __restrict__ parts, int n_parts, float2* __r
   pdl_wait();  // launched as a programmatic dependent of the GEMM that wrote `parts`
   if (row >= M) return;
   float s1 = 0.f, s2 = 0.f;
-  // eight independent loads in flight per thread (one dependent load per iteration runs at a third of the copy rate:
-  // 9 us for the 19 MB of a 100352-row ViT-B step, 24 times per step); the adds stay in index order
+  // all loads of a row in flight together, eight at a time (2 * N / BN partials: 6 for the 256-wide tiles of a ViT-B
+  // step, up to 32 with 64-wide tiles); the adds stay in index order.  The kernel moves a few MB: it is bound by its
+  // launch and by this one round trip to L2, not by bandwidth.
   const float2* src = parts + row;
-  int i = 0;
-  for (; i + 8 <= n_parts; i += 8) {
+  for (int i = 0; i < n_parts; i += 8) {
     float2 v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldg(&src[static_cast<size_t>(i + k) * M]);
+    for (int k = 0; k < 8; ++k)
+      v[k] = (i + k < n_parts) ? __ldg(&src[static_cast<size_t>(i + k) * M]) : make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      s1 += v[k].x;
-      s2 += v[k].y;
+      if (i + k < n_parts) {  // (adding the zeros of absent parts would turn a -0 sum into +0)
+        s1 += v[k].x;
+        s2 += v[k].y;
+      }
     }
-  }
-  for (; i < n_parts; ++i) {
-    const float2 v = __ldg(&src[static_cast<size_t>(i) * M]);
-    s1 += v.x;
-    s2 += v.y;
   }
   const float mean = s1 * inv_d;
   const float var = fmaxf(fmaf(-mean, mean, s2 * inv_d), 0.f);
