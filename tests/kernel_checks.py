@@ -495,6 +495,14 @@ CHECKS = {
     "attention_ragged": lambda: [check_attention(1, 1, 32), check_attention(2, 2, 100), check_attention(1, 2, 129),
                                  check_attention(1, 1, 255), check_attention(2, 1, 257), check_attention(1, 3, 300),
                                  check_attention(1, 2, 640, peaky=4.0)],
+    # one row, one row short of / past a 128-row tile, N with 64 as its only tile width (320), a single k-block
+    "gemm_edges": lambda: [check_gemm(M, N, K, mode, seed=40 + i) for i, (M, N, K, mode) in enumerate(
+        ((1, 64, 64, "bias"), (127, 320, 128, "resid"), (129, 192, 64, "ln"), (255, 320, 192, "ln_gelu"),
+         (1, 768, 768, "resid"), (385, 64, 3072, "plain")))],
+    # sequence lengths at the seams of the unit / tile geometry: fewer keys than one 32-key chunk, a 1-key ragged tile
+    # (97, 193), exact multiples of the 96-key tile, a 33-row tail (one row too many for the key-split unit), 1 token
+    "attention_edges": lambda: [check_attention(2, 2, S, seed=30 + i) for i, S in
+                                enumerate((1, 7, 31, 33, 64, 96, 97, 128, 192, 193, 289, 384))],
     # more work units than SMs: every CTA of the persistent kernel loops over several units (phase bookkeeping)
     "attention_persistent": lambda: [check_attention(5, 12, 1568, seed=3), check_attention(40, 12, 160, seed=4),
                                      check_attention(16, 6, 392, peaky=5.0, seed=5)],
