@@ -4,7 +4,8 @@ itself is absent (the GPU box): `build()` — called by __graft_entry__.build() 
 imports) byte for byte into the git-ignored oracle/_ref/, which travels to the GPU box like the built libstad.so.
 `load()` imports modeling_finetune from there behind the same 4-symbol `timm` shim oracle/make_golden.py uses (timm is
 not installed; the shim does not touch the forward math).  Nothing in simple-tad_b200/ imports this; only
-bench.py's `--impl reference` / cpu_baseline legs do."""
+bench.py's `--impl reference` / cpu_baseline legs and tests/test_model_gpu.py (the live comparison with the reference
+executed on the GPU box) do."""
 import filecmp
 import os
 import shutil

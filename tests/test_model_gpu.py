@@ -136,6 +136,54 @@ def test_config2_vitb_sliding_window_video():
     assert float((logits - direct).abs().max()) <= 5e-3, float((logits - direct).abs().max())
 
 
+@pytest.mark.parametrize("arch,n_windows,seed,trained", [
+    ("vit_base_patch16_224", 64, 4242, False),     # the bench step: 64 stride-1 windows of a 79-frame video
+    ("vit_small_patch16_224", 64, 4243, False),
+    ("vit_large_patch16_224", 16, 4244, False),
+    ("vit_base_patch16_224", 16, 4245, True),      # trained-like statistics + layer scale
+])
+def test_live_unmodified_reference_on_this_gpu(arch, n_windows, seed, trained):
+    """Seeds no fixture was made from: the UNMODIFIED reference (oracle/_ref/modeling_finetune.py, fp32, eager attention,
+    TF32 off) runs on this GPU on the same weights and windows, at the bench's batch for ViT-B; the kernels must stay
+    within BASELINE's tolerance on every window.  Skipped where the build step could not copy the reference files."""
+    from functools import partial
+    from oracle import ref_loader
+    mf_ref = ref_loader.load()
+    if mf_ref is None:
+        pytest.skip("oracle/_ref not present (built where /root/reference exists)")
+    sd = synth.make_trained_like_state_dict(arch, seed=seed) if trained else synth.make_state_dict(arch, seed=seed)
+    frames = synth.make_video(n_windows + 15, seed=seed)
+    D, depth, heads = synth.ARCHS[arch]
+    kw = dict(init_values=0.1) if trained else {}
+    ref = mf_ref.VisionTransformer(patch_size=16, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
+                                   norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=2, all_frames=16,
+                                   tubelet_size=2, init_scale=1.0, final_reduction="fc_norm", use_flash_attn=False, **kw)
+    ref.load_state_dict(sd, strict=True)
+    ref = ref.to(DEV).eval()
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        clips = synth.windows_from_video(frames, start=0, count=n_windows)
+        want = []
+        with torch.no_grad():
+            for i in range(0, n_windows, 8):  # the eager S x S scores of 8 clips x 12-16 heads are ~1 GB in fp32
+                want.append(ref(clips[i:i + 8].to(DEV)).float().cpu())
+        want = torch.cat(want)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    del ref
+    torch.cuda.empty_cache()
+    from simple_tad_b200 import modeling_finetune as mf
+    model = mf.VisionTransformer(patch_size=16, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
+                                 norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_classes=2, all_frames=16,
+                                 tubelet_size=2, init_scale=1.0, final_reduction="fc_norm", **kw)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    logits, _ = model.forward_windows(frames.to(DEV), start=0, count=n_windows)
+    res = parity.check_logits(logits, want, f"live reference, {arch}, {n_windows} windows, seed {seed}, trained-like={trained}")
+    print(res)  # (pytest -s: the measured max|dp| / cosines go to profiles/)
+
+
 def test_config3_vitl_two_videos():
     """BASELINE config 3 (single-GPU part): ViT-L/16 sliding windows (2 videos x 20 frames -> 10 windows)."""
     g = parity.golden("c3_vitl_2x20")
