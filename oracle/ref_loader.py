@@ -1,7 +1,7 @@
 """TEST / BASELINE INFRASTRUCTURE ONLY.  Makes the UNMODIFIED reference modules importable where the reference checkout
 itself is absent (the GPU box): `build()` — called by __graft_entry__.build() in the build container, where
-/root/reference exists — copies the two files of the path (modeling_finetune.py and the flash_attention_class.py it
-imports) byte for byte into the git-ignored oracle/_ref/, which travels to the GPU box like the built libstad.so.
+/root/reference exists — copies the files of the path (modeling_finetune.py, the flash_attention_class.py it imports, and
+modeling_pretrain.py for the masked encoder / MAE forward) byte for byte into the git-ignored oracle/_ref/, which travels to the GPU box like the built libstad.so.
 `load()` imports modeling_finetune from there behind the same 4-symbol `timm` shim oracle/make_golden.py uses (timm is
 not installed; the shim does not touch the forward math).  Nothing in simple-tad_b200/ imports this; only
 bench.py's `--impl reference` / cpu_baseline legs and tests/test_model_gpu.py (the live comparison with the reference
@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
-REF_FILES = ("modeling_finetune.py", "flash_attention_class.py")
+REF_FILES = ("modeling_finetune.py", "flash_attention_class.py", "modeling_pretrain.py")
 
 
 def build(reference="/root/reference"):
@@ -28,9 +28,9 @@ def build(reference="/root/reference"):
     return all(os.path.exists(os.path.join(REF_DIR, f)) for f in REF_FILES)
 
 
-def load():
-    """The reference's modeling_finetune module imported from oracle/_ref/, or None (files absent / an import of theirs
-    unavailable on this box)."""
+def load(module="modeling_finetune"):
+    """The reference's modeling_finetune (or modeling_pretrain) module imported from oracle/_ref/, or None (files absent /
+    an import of theirs unavailable on this box)."""
     if not all(os.path.exists(os.path.join(REF_DIR, f)) for f in REF_FILES):
         return None
     from . import make_golden
@@ -38,7 +38,7 @@ def load():
     try:
         make_golden.install_shims(ref_path=REF_DIR)
         import importlib
-        return importlib.import_module("modeling_finetune")
+        return importlib.import_module(module)
     except Exception as e:  # noqa: BLE001  (e.g. flash_attn not importable on a CPU-only box)
         sys.stderr.write(f"oracle/_ref: reference modules not importable here ({e!r}); using the port\n")
         sys.path[:] = saved

@@ -184,6 +184,60 @@ def test_live_unmodified_reference_on_this_gpu(arch, n_windows, seed, trained):
     print(res)  # (pytest -s: the measured max|dp| / cosines go to profiles/)
 
 
+def test_live_unmodified_reference_masked_encoder_and_mae_on_this_gpu():
+    """BASELINE config 4 against the UNMODIFIED modeling_pretrain.py executed on this GPU (fp32, eager attention, TF32 off)
+    on fresh seeds: the DAPT encoder on 32 clips with 90 % tube masking (every visible token of every clip) and the full
+    MAE pre-training forward on 8 clips (every predicted pixel row)."""
+    from functools import partial
+    from oracle import ref_loader
+    mp_ref = ref_loader.load("modeling_pretrain")
+    if mp_ref is None:
+        pytest.skip("oracle/_ref not present (built where /root/reference exists)")
+    arch = "vit_base_patch16_224"
+    D, depth, heads = synth.ARCHS[arch]
+    Dd, dheads = synth.DECODERS[arch]
+    norm = partial(torch.nn.LayerNorm, eps=1e-6)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        # ---- encoder
+        sd = synth.make_state_dict(arch, seed=5150, encoder=True)
+        x, mask = synth.make_clips(32, seed=5150), synth.tube_mask(32, 0.9, seed=5150)
+        ref = mp_ref.PretrainVisionTransformerEncoder(
+            img_size=224, patch_size=16, in_chans=3, num_classes=0, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4,
+            qkv_bias=True, norm_layer=norm, init_values=0., tubelet_size=2, use_flash_attn=False)
+        ref.load_state_dict(sd, strict=True)
+        ref = ref.to(DEV).eval()
+        with torch.no_grad():
+            want = torch.cat([ref(x[i:i + 8].to(DEV), mask[i:i + 8].to(DEV)).float().cpu() for i in range(0, 32, 8)])
+        del ref
+        y = parity.build_encoder(arch, sd)(x.to(DEV), mask.to(DEV)).float().cpu()
+        assert y.shape == want.shape == (32, 160, D)
+        cos, rel = parity.row_cosine_min(y, want), float((y - want).norm() / want.norm())
+        print({"what": "live reference, DAPT encoder ViT-B, 32 clips", "cos_row_min": cos, "rel_l2": rel})
+        assert cos >= parity.TOL_COS and rel <= parity.TOL_HIDDEN_REL_L2, (cos, rel)
+        # ---- full pre-training forward
+        sdm = synth.make_pretrain_state_dict(arch, seed=5151, decoder_depth=4)
+        xm, mm = synth.make_clips(8, seed=5151), synth.tube_mask(8, 0.9, seed=5151)
+        refm = mp_ref.PretrainVisionTransformer(
+            img_size=224, patch_size=16, encoder_embed_dim=D, encoder_depth=depth, encoder_num_heads=heads,
+            encoder_num_classes=0, decoder_num_classes=1536, decoder_embed_dim=Dd, decoder_num_heads=dheads,
+            decoder_depth=4, mlp_ratio=4, qkv_bias=True, norm_layer=norm, use_flash_attn=False)
+        refm.load_state_dict(sdm, strict=True)
+        refm = refm.to(DEV).eval()
+        with torch.no_grad():
+            wantm = torch.cat([refm(xm[i:i + 2].to(DEV), mm[i:i + 2].to(DEV)).float().cpu() for i in range(0, 8, 2)])
+        del refm
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.cuda.empty_cache()
+    ym = parity.build_pretrain(arch, sdm, decoder_depth=4)(xm.to(DEV), mm.to(DEV)).float().cpu()
+    assert ym.shape == wantm.shape == (8, 1408, 1536)
+    cosm, relm = parity.row_cosine_min(ym, wantm), float((ym - wantm).norm() / wantm.norm())
+    print({"what": "live reference, MAE forward ViT-B + 4 decoder blocks, 8 clips", "cos_row_min": cosm, "rel_l2": relm})
+    assert cosm >= parity.TOL_COS and relm <= parity.TOL_HIDDEN_REL_L2, (cosm, relm)
+
+
 def test_config3_vitl_two_videos():
     """BASELINE config 3 (single-GPU part): ViT-L/16 sliding windows (2 videos x 20 frames -> 10 windows)."""
     g = parity.golden("c3_vitl_2x20")
