@@ -238,6 +238,66 @@ def test_live_unmodified_reference_masked_encoder_and_mae_on_this_gpu():
     assert cosm >= parity.TOL_COS and relm <= parity.TOL_HIDDEN_REL_L2, (cosm, relm)
 
 
+def test_faster_than_the_reference_gpu_stack_on_this_box():
+    """Context for the headline, measured not assumed: the UNMODIFIED reference on this same GPU the way its own
+    evaluation loop runs it — `torch.cuda.amp.autocast()` (fp16) with flash-attn 2 (eff:428, mf:121-128) — and in eager
+    attention, on 64 ViT-B clips per step; the kernels of this repo on the same 64 windows.  CUDA events, 3 warm-up + 8
+    timed steps each.  The assertion is deliberately loose (1.3 x); the measured ratio is printed (pytest -s)."""
+    from oracle import ref_loader
+    mf_ref = ref_loader.load()
+    if mf_ref is None:
+        pytest.skip("oracle/_ref not present (built where /root/reference exists)")
+    arch, B = "vit_base_patch16_224", 64
+    sd = synth.make_state_dict(arch, seed=77)
+    frames = synth.make_video(B + 15, seed=77)
+    clips = synth.windows_from_video(frames, start=0, count=B).to(DEV)
+
+    def timed(fn, warm=3, iters=8):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    out = {}
+    for flash in (True, False):
+        try:
+            ref = mf_ref.__dict__[arch](num_classes=2, all_frames=16, tubelet_size=2, use_flash_attn=flash, init_scale=1.0,
+                                        final_reduction="fc_norm")
+            ref.load_state_dict(sd, strict=True)
+            ref = ref.to(DEV).eval()
+
+            @torch.no_grad()
+            def step():
+                with torch.autocast("cuda", dtype=torch.float16):  # = torch.cuda.amp.autocast() of eff:428
+                    if flash:
+                        return ref(clips)
+                    return torch.cat([ref(clips[i:i + 16]) for i in range(0, B, 16)])  # eager scores: 16 clips at a time
+            out["flash-attn 2" if flash else "eager attention"] = (timed(step), step().float().cpu())
+            del ref
+        except Exception as e:  # noqa: BLE001  (flash-attn unavailable on the box: the eager leg still stands)
+            print(f"reference GPU leg (flash={flash}) not runnable here: {e!r}")
+        torch.cuda.empty_cache()
+    assert out, "no reference GPU leg ran"
+    model = parity.build_classifier(arch, sd)
+    dev_frames = frames.to(DEV)
+    ours_ms = timed(lambda: model.forward_windows(dev_frames, start=0, count=B))
+    logits, _ = model.forward_windows(dev_frames, start=0, count=B)
+    for name, (ms, ref_logits) in out.items():
+        dp = float((logits.float().cpu().softmax(-1) - ref_logits.softmax(-1)).abs().max())
+        print({"reference GPU path": f"autocast fp16 + {name}", "ref_ms_per_64_clips": ms, "ref_clips_per_s": 1e3 * B / ms,
+               "ours_ms_per_64_windows": ours_ms, "ours_clips_per_s": 1e3 * B / ours_ms, "speedup": ms / ours_ms,
+               "max_dp_between_the_two": dp})
+        assert dp <= parity.TOL_DP, (name, dp)
+    best_ref = min(ms for ms, _ in out.values())
+    assert best_ref / ours_ms >= 1.3, f"reference GPU stack {best_ref:.2f} ms vs ours {ours_ms:.2f} ms per 64 clips"
+
+
 def test_config3_vitl_two_videos():
     """BASELINE config 3 (single-GPU part): ViT-L/16 sliding windows (2 videos x 20 frames -> 10 windows)."""
     g = parity.golden("c3_vitl_2x20")
