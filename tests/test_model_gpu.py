@@ -298,6 +298,61 @@ def test_faster_than_the_reference_gpu_stack_on_this_box():
     assert best_ref / ours_ms >= 1.3, f"reference GPU stack {best_ref:.2f} ms vs ours {ours_ms:.2f} ms per 64 clips"
 
 
+def test_dapt_encoder_faster_than_the_reference_gpu_stack_on_this_box():
+    """As above for BASELINE config 4: the unmodified PretrainVisionTransformerEncoder under fp16 autocast with flash-attn 2
+    (the reference's pre-training configuration) on 100 clips with 90 % tube masking, next to this repo's encoder."""
+    from functools import partial
+    from oracle import ref_loader
+    mp_ref = ref_loader.load("modeling_pretrain")
+    if mp_ref is None:
+        pytest.skip("oracle/_ref not present (built where /root/reference exists)")
+    arch, B = "vit_base_patch16_224", 100
+    D, depth, heads = synth.ARCHS[arch]
+    sd = synth.make_state_dict(arch, seed=78, encoder=True)
+    x = synth.make_clips(B, seed=78).to(DEV)
+    mask = synth.tube_mask(B, 0.9, seed=78).to(DEV)
+
+    def timed(fn, warm=3, iters=10):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    try:
+        ref = mp_ref.PretrainVisionTransformerEncoder(
+            img_size=224, patch_size=16, in_chans=3, num_classes=0, embed_dim=D, depth=depth, num_heads=heads, mlp_ratio=4,
+            qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), init_values=0., tubelet_size=2,
+            use_flash_attn=True)
+        ref.load_state_dict(sd, strict=True)
+        ref = ref.to(DEV).eval()
+
+        @torch.no_grad()
+        def step():
+            with torch.autocast("cuda", dtype=torch.float16):
+                return ref(x, mask)
+        ref_ms, want = timed(step), step().float().cpu()
+        del ref
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"reference GPU leg not runnable here: {e!r}")
+    torch.cuda.empty_cache()
+    enc = parity.build_encoder(arch, sd)
+    xb = x.to(torch.bfloat16)
+    ours_ms = timed(lambda: enc(xb, mask, n_visible=160))
+    y = enc(xb, mask, n_visible=160).float().cpu()
+    rel = float((y - want).norm() / want.norm())
+    print({"reference GPU path": "DAPT encoder, autocast fp16 + flash-attn 2", "ref_ms_per_100_clips": ref_ms,
+           "ref_clips_per_s": 1e3 * B / ref_ms, "ours_ms_per_100_clips": ours_ms, "ours_clips_per_s": 1e3 * B / ours_ms,
+           "speedup": ref_ms / ours_ms, "rel_l2_between_the_two": rel})
+    assert rel <= parity.TOL_HIDDEN_REL_L2, rel
+    assert ref_ms / ours_ms >= 1.3, f"reference GPU stack {ref_ms:.2f} ms vs ours {ours_ms:.2f} ms per 100 clips"
+
+
 def test_config3_vitl_two_videos():
     """BASELINE config 3 (single-GPU part): ViT-L/16 sliding windows (2 videos x 20 frames -> 10 windows)."""
     g = parity.golden("c3_vitl_2x20")
