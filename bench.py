@@ -155,7 +155,8 @@ def cpu_forward_setup(model_name):
     return run, synth, "port"
 
 
-def cpu_baseline(model_name, clips=2, repeats=2):
+def cpu_baseline(model_name, clips=8, repeats=5):
+    """Bounded sample of the workload on the host cores: ~10 s of CPU work (5 forwards of 8 clips at 3-6 clips/s)."""
     run, synth, kind = cpu_forward_setup(model_name)
     x = synth.make_clips(clips, seed=123)
     run(x[:1])  # warm-up (thread pool, oneDNN primitives)
